@@ -1,0 +1,745 @@
+// pyh_api.cu -- context, memory management and the extern "C" entry points of include/pyh_b200.h
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <string>
+
+#include "pyh_kernels.cuh"
+
+using namespace pyh;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return set_err(PYH_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                           cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+namespace {
+
+struct HostBlock {
+    pyh_block_desc d;   // pointers inside are NOT retained
+    BlkDev dev;
+    std::vector<void*> allocs;
+};
+
+struct Ctx {
+    pyh_config cfg;
+    Layout lay;
+    Consts C;
+    Tableau tab;
+    cudaStream_t stream = nullptr;
+    std::vector<HostBlock> blocks;
+    std::map<int, int> gid2idx;
+    BlkDev* d_blks = nullptr;
+    Control* d_ctl = nullptr;
+    HaloSlot* d_slots = nullptr;
+    std::vector<HaloSlot> slots;
+    std::vector<int> slot_nbr_gid;
+    long long halo_doubles = 0;
+    bool finalized = false;
+    int i0 = 0, i1 = 1, i2 = 2;   // roles of the three haloed buffers; H[i0] holds the current solution
+    int cur = 0;                   // buffer read by the next stage
+    int stage_next = 0;
+    bool need_acc[PYH_MAX_STAGES];
+    long long launches = 0;
+    double* d_scratch = nullptr;   // staging for uploads/downloads
+    size_t scratch_bytes = 0;
+    double* d_dts = nullptr;
+    long long dts_cap = 0;
+    double* d_tmp = nullptr;       // small device scratch (dt etc.)
+    int tile_kind = 0;
+};
+
+int ensure_scratch(Ctx* c, size_t bytes) {
+    if (c->scratch_bytes >= bytes) return 0;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    CU(cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return 0;
+}
+
+int dalloc(HostBlock& hb, double** p, long long ndoubles, bool zero) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (size_t)ndoubles * sizeof(double));
+    if (e != cudaSuccess) return set_err(PYH_ERR_NOMEM, "cudaMalloc of %lld doubles failed: %s", ndoubles, cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemset(q, 0, (size_t)ndoubles * sizeof(double));
+        if (e != cudaSuccess) return set_err(PYH_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    hb.allocs.push_back(q);
+    *p = (double*)q;
+    return 0;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- stage kernel dispatch ------------------------------------------------------------------------
+constexpr int TX = 32, TY = 8, NT = 256;
+typedef void (*StageFn)(const BlkDev*, Layout, StagePlan, const Control*, Consts, int);
+
+template <int F, int L, int P>
+StageFn stage_fn() { return k_stage_tile<F, L, P, TX, TY, NT>; }
+
+template <int F, int L>
+StageFn pick_p(int p) { return p ? stage_fn<F, L, 1>() : stage_fn<F, L, 0>(); }
+template <int F>
+StageFn pick_l(int l, int p) {
+    switch (l) {
+        case 0: return pick_p<F, 0>(p);
+        case 1: return pick_p<F, 1>(p);
+        case 2: return pick_p<F, 2>(p);
+        default: return pick_p<F, 3>(p);
+    }
+}
+StageFn pick_stage(int f, int l, int p) {
+    switch (f) {
+        case 0: return pick_l<0>(l, p);
+        case 1: return pick_l<1>(l, p);
+        default: return pick_l<2>(l, p);
+    }
+}
+
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
+    StageFn fn = pick_stage(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
+    size_t smem = TileShape<TX, TY>::SMEM_DOUBLES * sizeof(double);
+    static thread_local StageFn configured[64];
+    static thread_local int nconf = 0;
+    bool done = false;
+    for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
+    if (!done) {
+        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (nconf < 64) configured[nconf++] = fn;
+    }
+    dim3 grid(cdiv(c->lay.nx, TX), cdiv(c->lay.ny, TY), (unsigned)c->blocks.size());
+    fn<<<grid, NT, smem, c->stream>>>(c->d_blks, c->lay, plan, c->d_ctl, c->C, want_grad_dbg);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+// RK partial-sum plan for stage s (explicit_runge_kutta.py:63-75 restated as running sums:
+// row s' accumulates U0 + sum_{k<=s} (dt*a[s'][k]) R_k in k order, exactly the reference's order)
+StagePlan make_plan(Ctx* c, int s, int cur, int next) {
+    StagePlan p;
+    memset(&p, 0, sizeof(p));
+    p.cur = cur; p.next = next; p.u0 = c->i0;
+    const int S = c->cfg.num_stages;
+    auto a = [&](int r, int k) { return c->tab.a[r * PYH_MAX_STAGES + k]; };
+    for (int r = s; r < S; ++r) {
+        bool prior = false;
+        for (int k = 0; k < s; ++k) if (a(r, k) != 0.0) prior = true;
+        bool nz = a(r, s) != 0.0;
+        if (r == s) {
+            RkTarget t;
+            t.src = prior ? 1 : 0; t.dst = 0; t.row = r; t.add = nz ? 1 : 0; t.coef = r * PYH_MAX_STAGES + s;
+            p.t[p.ntargets++] = t;
+        } else if (nz) {
+            RkTarget t;
+            t.src = prior ? 1 : 0; t.dst = 1; t.row = r; t.add = 1; t.coef = r * PYH_MAX_STAGES + s;
+            p.t[p.ntargets++] = t;
+        }
+    }
+    return p;
+}
+
+int do_ghost(Ctx* c, int buf) {
+    int m = std::max(c->lay.nx, c->lay.ny);
+    dim3 grid(cdiv(m, 128), 4, (unsigned)c->blocks.size());
+    k_ghost<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, buf, c->d_ctl);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int do_stage(Ctx* c, int s) {
+    const int S = c->cfg.num_stages;
+    int cur = (s == 0) ? c->i0 : c->cur;
+    int next;
+    if (s == S - 1) next = (S == 1) ? c->i1 : c->i0;
+    else next = (cur == c->i1) ? c->i2 : c->i1;
+    StagePlan p = make_plan(c, s, cur, next);
+    int rc = launch_stage(c, p, 0);
+    if (rc) return rc;
+    c->cur = next;
+    if (s == S - 1) {
+        if (S == 1) std::swap(c->i0, c->i1);
+        c->cur = c->i0;
+    }
+    return 0;
+}
+
+int set_active(Ctx* c, int active) {
+    CU(cudaMemcpyAsync(&c->d_ctl->active, &active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int launch_dt(Ctx* c, int buf, int respect_active = 0) {
+    long long total = (long long)c->lay.nx * c->lay.ny * (long long)c->blocks.size();
+    int grid = (int)std::min<long long>(cdiv(total, 256), 148 * 8);
+    k_dt<<<grid, 256, 0, c->stream>>>(c->d_blks, c->lay, buf, (int)c->blocks.size(), c->d_ctl, c->C, respect_active);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+Ctx* as_ctx(void* p) { return reinterpret_cast<Ctx*>(p); }
+
+}  // namespace
+
+extern "C" {
+
+const char* pyh_last_error(void) { return g_err; }
+int pyh_abi_version(void) { return PYH_ABI_VERSION; }
+
+int pyh_create(const pyh_config* cfg, void** out) {
+    if (!cfg || !out) return set_err(PYH_ERR_INVALID, "null argument");
+    if (cfg->abi_version != PYH_ABI_VERSION) return set_err(PYH_ERR_INVALID, "ABI version mismatch: got %d, library is %d", cfg->abi_version, PYH_ABI_VERSION);
+    if (cfg->nx < 1 || cfg->ny < 1) return set_err(PYH_ERR_INVALID, "nx, ny must be >= 1");
+    if (cfg->flux < 0 || cfg->flux > 2) return set_err(PYH_ERR_INVALID, "unknown flux function %d", cfg->flux);
+    if (cfg->limiter < 0 || cfg->limiter > 3) return set_err(PYH_ERR_INVALID, "unknown slope limiter %d", cfg->limiter);
+    if (cfg->recon < 0 || cfg->recon > 1) return set_err(PYH_ERR_INVALID, "unknown reconstruction type %d", cfg->recon);
+    if (cfg->num_quadrature_points != 1) return set_err(PYH_ERR_INVALID, "only fvm_num_quadrature_points == 1 is implemented on the device (got %d)", cfg->num_quadrature_points);
+    if (cfg->num_stages < 1 || cfg->num_stages > PYH_MAX_STAGES) return set_err(PYH_ERR_INVALID, "num_stages must be in 1..%d", PYH_MAX_STAGES);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err(PYH_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    Ctx* c = new Ctx();
+    c->cfg = *cfg;
+    c->lay.nx = cfg->nx; c->lay.ny = cfg->ny;
+    c->lay.pitch = ((cfg->nx + PADL + 1 + 3) / 4) * 4;
+    c->lay.plane = (long long)(cfg->ny + 2) * c->lay.pitch;
+    c->C.g = cfg->gamma;
+    c->C.gm1 = cfg->gamma - 1.0;
+    c->C.k = 1.0 / (cfg->gamma - 1.0);
+    c->C.gm = cfg->gamma / (cfg->gamma - 1.0);
+    memset(&c->tab, 0, sizeof(c->tab));
+    c->tab.nstages = cfg->num_stages;
+    for (int s = 0; s < cfg->num_stages; ++s)
+        for (int k = 0; k <= s; ++k) c->tab.a[s * PYH_MAX_STAGES + k] = cfg->tableau[s * PYH_MAX_STAGES + k];
+    for (int r = 0; r < PYH_MAX_STAGES; ++r) {
+        c->need_acc[r] = false;
+        for (int k = 0; k < r && r < cfg->num_stages; ++k)
+            if (c->tab.a[r * PYH_MAX_STAGES + k] != 0.0) c->need_acc[r] = true;
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
+    Control h;
+    memset(&h, 0, sizeof(h));
+    h.dtmin_bits = DKEY_INF;
+    h.active = 1;
+    CU(cudaMemcpy(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_tmp, 64 * sizeof(double)));
+    *out = c;
+    return 0;
+}
+
+int pyh_add_block(void* ctx, const pyh_block_desc* b) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !b) return set_err(PYH_ERR_INVALID, "null argument");
+    if (c->finalized) return set_err(PYH_ERR_STATE, "pyh_add_block after pyh_finalize");
+    if (c->gid2idx.count(b->gid)) return set_err(PYH_ERR_INVALID, "block %d added twice", b->gid);
+    if (!b->nodes_x || !b->nodes_y || !b->area || !b->cos_v || !b->sin_v || !b->cos_h || !b->sin_h)
+        return set_err(PYH_ERR_INVALID, "block %d: null geometry pointer", b->gid);
+    for (int s = 0; s < 4; ++s) {
+        if (b->bc[s] < 0 || b->bc[s] > PYH_BC_PRIMITIVE_DIRICHLET) return set_err(PYH_ERR_INVALID, "Boundary Condition type %d has not been specialized.", b->bc[s]);
+        if (b->bc[s] == PYH_BC_PRIMITIVE_DIRICHLET && !b->dirichlet_prim[s]) return set_err(PYH_ERR_INVALID, "block %d side %d: Dirichlet BC without inlet state", b->gid, s);
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    const Layout& L = c->lay;
+    const int nx = L.nx, ny = L.ny;
+    HostBlock hb;
+    hb.d = *b;
+    memset(&hb.dev, 0, sizeof(hb.dev));
+    BlkDev& D = hb.dev;
+    int rc;
+    for (int h = 0; h < 3; ++h) {
+        if (h == 2 && c->cfg.num_stages < 3) { D.H[h] = nullptr; continue; }
+        if ((rc = dalloc(hb, &D.H[h], 4 * L.plane, true))) return rc;
+    }
+    for (int r = 0; r < c->cfg.num_stages; ++r)
+        if (c->need_acc[r]) { if ((rc = dalloc(hb, &D.P[r], 4 * L.plane, true))) return rc; }
+    double *A, *dxy, *Lv, *cv, *sv, *Lh, *ch, *sh, *cdx, *cdy;
+    if ((rc = dalloc(hb, &A, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &dxy, 8 * L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &Lv, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &cv, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &sv, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &Lh, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &ch, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &sh, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &cdx, L.plane, true))) return rc;
+    if ((rc = dalloc(hb, &cdy, L.plane, true))) return rc;
+    // stage host arrays through the scratch buffer
+    size_t nn = (size_t)(ny + 1) * (nx + 1);
+    if ((rc = ensure_scratch(c, 2 * nn * sizeof(double)))) return rc;
+    auto put = [&](const double* host, double* plane, int rows, int cols) -> int {
+        size_t n = (size_t)rows * cols;
+        CU(cudaMemcpyAsync(c->d_scratch, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        k_dense_to_plane<<<cdiv(n, 256), 256, 0, c->stream>>>(L, c->d_scratch, plane, rows, cols);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    if ((rc = put(b->area, A, ny, nx))) return rc;
+    if ((rc = put(b->cos_v, cv, ny, nx + 1))) return rc;
+    if ((rc = put(b->sin_v, sv, ny, nx + 1))) return rc;
+    if ((rc = put(b->cos_h, ch, ny + 1, nx))) return rc;
+    if ((rc = put(b->sin_h, sh, ny + 1, nx))) return rc;
+    CU(cudaMemcpyAsync(c->d_scratch, b->nodes_x, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_scratch + nn, b->nodes_y, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    D.A = A; D.dxy = dxy; D.Lv = Lv; D.cv = cv; D.sv = sv; D.Lh = Lh; D.ch = ch; D.sh = sh; D.cdx = cdx; D.cdy = cdy;
+    if ((rc = dalloc(hb, &D.dbg, 4 * L.plane, true))) return rc;
+    for (int s = 0; s < 4; ++s) {
+        D.bc[s] = b->bc[s];
+        D.nbr[s] = -1;
+        D.remote_slot[s] = -1;
+        D.dir_recon[s] = nullptr;
+        D.dir_cons[s] = nullptr;
+        if (b->bc[s] == PYH_BC_PRIMITIVE_DIRICHLET) {
+            int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
+            double *prim, *recon, *cons;
+            if ((rc = dalloc(hb, &prim, 4 * len, false))) return rc;
+            if ((rc = dalloc(hb, &recon, 4 * len, false))) return rc;
+            if ((rc = dalloc(hb, &cons, 4 * len, false))) return rc;
+            CU(cudaMemcpy(prim, b->dirichlet_prim[s], 4 * (size_t)len * sizeof(double), cudaMemcpyHostToDevice));
+            k_dirichlet<<<cdiv(len, 128), 128, 0, c->stream>>>(prim, recon, cons, len, c->cfg.recon, c->C);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+            D.dir_recon[s] = recon;
+            D.dir_cons[s] = cons;
+        }
+    }
+    D.cart = b->is_cartesian;
+    D.gid = b->gid;
+    hb.d.nodes_x = hb.d.nodes_y = hb.d.area = hb.d.cos_v = hb.d.sin_v = hb.d.cos_h = hb.d.sin_h = nullptr;
+    for (int s = 0; s < 4; ++s) hb.d.dirichlet_prim[s] = nullptr;
+    c->gid2idx[b->gid] = (int)c->blocks.size();
+    c->blocks.push_back(hb);
+    return 0;
+}
+
+int pyh_finalize(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return set_err(PYH_ERR_INVALID, "null context");
+    if (c->finalized) return set_err(PYH_ERR_STATE, "pyh_finalize called twice");
+    if (c->blocks.empty()) return set_err(PYH_ERR_STATE, "no blocks");
+    CU(cudaSetDevice(c->cfg.device));
+    // halo slots in (gid, side) ascending order
+    std::vector<std::pair<int, int>> order;
+    for (auto& kv : c->gid2idx) order.push_back({kv.first, kv.second});
+    std::sort(order.begin(), order.end());
+    c->slots.clear();
+    c->halo_doubles = 0;
+    for (auto& pr : order) {
+        HostBlock& hb = c->blocks[pr.second];
+        for (int s = 0; s < 4; ++s) {
+            int ng = hb.d.neighbor[s];
+            hb.dev.nbr[s] = -1;
+            hb.dev.remote_slot[s] = -1;
+            if (ng < 0) continue;
+            if (hb.d.neighbor_is_local[s]) {
+                auto it = c->gid2idx.find(ng);
+                if (it == c->gid2idx.end()) return set_err(PYH_ERR_INVALID, "block %d: local neighbour %d was not added", hb.d.gid, ng);
+                hb.dev.nbr[s] = it->second;
+            } else if (hb.d.bc[s] == PYH_BC_NONE) {
+                int len = (s == PYH_EAST || s == PYH_WEST) ? c->lay.ny : c->lay.nx;
+                HaloSlot hs;
+                hs.blk = pr.second; hs.side = s; hs.offset = c->halo_doubles;
+                hb.dev.remote_slot[s] = (int)c->slots.size();
+                c->slots.push_back(hs);
+                c->slot_nbr_gid.push_back(ng);
+                c->halo_doubles += 4LL * len;
+            }
+        }
+    }
+    std::vector<BlkDev> tmp;
+    for (auto& hb : c->blocks) tmp.push_back(hb.dev);
+    CU(cudaMalloc(&c->d_blks, tmp.size() * sizeof(BlkDev)));
+    CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
+    if (!c->slots.empty()) {
+        CU(cudaMalloc(&c->d_slots, c->slots.size() * sizeof(HaloSlot)));
+        CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
+    }
+    c->finalized = true;
+    return 0;
+}
+
+int pyh_destroy(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& hb : c->blocks) {
+        for (void* p : hb.allocs) cudaFree(p);
+        if (hb.dev.dbgG) cudaFree(hb.dev.dbgG);
+    }
+    if (c->d_blks) cudaFree(c->d_blks);
+    if (c->d_ctl) cudaFree(c->d_ctl);
+    if (c->d_slots) cudaFree(c->d_slots);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_dts) cudaFree(c->d_dts);
+    if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+#define GET_BLOCK(c, gid, hb)                                                              \
+    if (!(c)) return set_err(PYH_ERR_INVALID, "null context");                             \
+    auto it_ = (c)->gid2idx.find(gid);                                                      \
+    if (it_ == (c)->gid2idx.end()) return set_err(PYH_ERR_INVALID, "unknown block %d", gid); \
+    HostBlock& hb = (c)->blocks[it_->second];                                               \
+    CU(cudaSetDevice((c)->cfg.device));
+
+int pyh_upload_state(void* ctx, int gid, const double* aos) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!aos) return set_err(PYH_ERR_INVALID, "null state pointer");
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    int rc = ensure_scratch(c, 4 * n * sizeof(double));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_scratch, aos, 4 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_aos_to_soa<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, c->d_scratch, hb.dev.H[c->i0]);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    return 0;
+}
+
+int pyh_download_state(void* ctx, int gid, double* aos) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!aos) return set_err(PYH_ERR_INVALID, "null state pointer");
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    int rc = ensure_scratch(c, 4 * n * sizeof(double));
+    if (rc) return rc;
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.H[c->i0], c->d_scratch, 4);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(aos, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    return 0;
+}
+
+int pyh_download_ghost(void* ctx, int gid, int side, double* out) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (side < 0 || side > 3 || !out) return set_err(PYH_ERR_INVALID, "bad side / null pointer");
+    int len = (side == PYH_EAST || side == PYH_WEST) ? c->lay.ny : c->lay.nx;
+    int rc = ensure_scratch(c, 4 * (size_t)len * sizeof(double));
+    if (rc) return rc;
+    k_ghost_strip_fetch<<<cdiv(len, 128), 128, 0, c->stream>>>(c->lay, hb.dev.H[c->i0], side, c->d_scratch);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_scratch, 4 * (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pyh_apply_bc(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = set_active(c, 1);
+    if (rc) return rc;
+    return do_ghost(c, c->cur);
+}
+
+int pyh_halo_count(void* ctx, int64_t* n_slots, int64_t* n_doubles) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (n_slots) *n_slots = (int64_t)c->slots.size();
+    if (n_doubles) *n_doubles = c->halo_doubles;
+    return 0;
+}
+
+int pyh_halo_slot(void* ctx, int64_t slot, int32_t* gid, int32_t* side, int32_t* nbr_gid, int64_t* offset, int64_t* len) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (slot < 0 || slot >= (int64_t)c->slots.size()) return set_err(PYH_ERR_INVALID, "slot out of range");
+    const HaloSlot& s = c->slots[slot];
+    if (gid) *gid = c->blocks[s.blk].d.gid;
+    if (side) *side = s.side;
+    if (nbr_gid) *nbr_gid = c->slot_nbr_gid[slot];
+    if (offset) *offset = s.offset;
+    if (len) *len = 4LL * ((s.side == PYH_EAST || s.side == PYH_WEST) ? c->lay.ny : c->lay.nx);
+    return 0;
+}
+
+int pyh_pack_halo(void* ctx, double* dev_send) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (c->slots.empty()) return 0;
+    CU(cudaSetDevice(c->cfg.device));
+    int m = std::max(c->lay.nx, c->lay.ny);
+    dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
+    k_pack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->cur, c->d_slots, dev_send);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pyh_unpack_halo(void* ctx, const double* dev_recv) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (c->slots.empty()) return 0;
+    CU(cudaSetDevice(c->cfg.device));
+    int m = std::max(c->lay.nx, c->lay.ny);
+    dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
+    k_unpack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->cur, c->d_slots, dev_recv);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pyh_local_dt(void* ctx, double* dev_dt_out) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = launch_dt(c, c->i0);
+    if (rc) return rc;
+    k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, dev_dt_out);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pyh_get_dt(void* ctx, double t, double t_final, double* dt_out) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !dt_out) return set_err(PYH_ERR_INVALID, "null pointer");
+    int rc = pyh_local_dt(ctx, c->d_tmp);
+    if (rc) return rc;
+    double dt;
+    CU(cudaMemcpyAsync(&dt, c->d_tmp, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *dt_out = (t_final - t < dt) ? (t_final - t) : dt;   // solvers/base.py:132-136
+    return 0;
+}
+
+int pyh_step_begin(void* ctx, double dt) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    CU(cudaSetDevice(c->cfg.device));
+    k_set_dt<<<1, 1, 0, c->stream>>>(c->d_ctl, dt, nullptr, c->tab);
+    CU(cudaGetLastError());
+    c->launches++;
+    c->stage_next = 0;
+    return 0;
+}
+
+int pyh_step_begin_dev(void* ctx, const double* dev_dt) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!dev_dt) return set_err(PYH_ERR_INVALID, "null pointer");
+    CU(cudaSetDevice(c->cfg.device));
+    k_set_dt<<<1, 1, 0, c->stream>>>(c->d_ctl, 0.0, dev_dt, c->tab);
+    CU(cudaGetLastError());
+    c->launches++;
+    c->stage_next = 0;
+    return 0;
+}
+
+int pyh_stage(void* ctx, int stage) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (stage != c->stage_next || stage >= c->cfg.num_stages) return set_err(PYH_ERR_STATE, "stage %d out of order (expected %d)", stage, c->stage_next);
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = do_stage(c, stage);
+    if (rc) return rc;
+    c->stage_next = stage + 1;
+    return 0;
+}
+
+int pyh_step(void* ctx, double dt) {
+    Ctx* c = as_ctx(ctx);
+    if (c && !c->slots.empty()) return set_err(PYH_ERR_STATE, "pyh_step on a context with remote neighbours; drive the stages from the host");
+    int rc = pyh_step_begin(ctx, dt);
+    if (rc) return rc;
+    for (int s = 0; s < c->cfg.num_stages; ++s) {
+        if ((rc = do_stage(c, s))) return rc;
+        if ((rc = do_ghost(c, c->cur))) return rc;
+    }
+    c->stage_next = c->cfg.num_stages;
+    return 0;
+}
+
+int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32_t poll_every,
+            int64_t* steps_done, int32_t* unrealizable, double* dts_out, int64_t dts_cap) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!t_inout) return set_err(PYH_ERR_INVALID, "null pointer");
+    if (!c->slots.empty()) return set_err(PYH_ERR_STATE, "pyh_run needs all neighbours local (single-rank context)");
+    CU(cudaSetDevice(c->cfg.device));
+    if (poll_every < 1) poll_every = 64;
+    if (max_steps < 0) max_steps = (int64_t)1 << 62;
+    if (dts_out && dts_cap > 0) {
+        if (c->dts_cap < dts_cap) {
+            if (c->d_dts) cudaFree(c->d_dts);
+            c->d_dts = nullptr;
+            CU(cudaMalloc(&c->d_dts, (size_t)dts_cap * sizeof(double)));
+            c->dts_cap = dts_cap;
+        }
+    }
+    Control h;
+    memset(&h, 0, sizeof(h));
+    h.t = *t_inout; h.t_final = t_final; h.dtmin_bits = DKEY_INF; h.active = 1; h.nsteps = 0; h.bad = 0;
+    CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    double* ddts = (dts_out && dts_cap > 0) ? c->d_dts : nullptr;
+    int64_t issued = 0;
+    int rc;
+    while (issued < max_steps) {
+        int64_t chunk = std::min<int64_t>(poll_every, max_steps - issued);
+        for (int64_t n = 0; n < chunk; ++n) {
+            if ((rc = launch_dt(c, c->i0, 1))) return rc;
+            k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 0, nullptr);
+            CU(cudaGetLastError());
+            for (int s = 0; s < c->cfg.num_stages; ++s) {
+                if ((rc = do_stage(c, s))) return rc;
+                if ((rc = do_ghost(c, c->cur))) return rc;
+            }
+            k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl, ddts, ddts ? dts_cap : 0);
+            CU(cudaGetLastError());
+            c->launches += 2;
+        }
+        issued += chunk;
+        CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (!h.active || h.bad || !(h.t < h.t_final)) break;
+    }
+    // final realizability check of the last state (Euler2D.py:204)
+    if ((rc = launch_dt(c, c->i0))) return rc;
+    k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, c->d_tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *t_inout = h.t;
+    if (steps_done) *steps_done = h.nsteps;
+    if (unrealizable) *unrealizable = h.bad;
+    if (ddts) {
+        int64_t n = std::min<int64_t>(h.nsteps, dts_cap);
+        if (n > 0) CU(cudaMemcpy(dts_out, c->d_dts, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    rc = set_active(c, 1);
+    return rc;
+}
+
+int pyh_realizable(void* ctx, int32_t* ok_out) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!ok_out) return set_err(PYH_ERR_INVALID, "null pointer");
+    CU(cudaSetDevice(c->cfg.device));
+    int zero = 0;
+    CU(cudaMemcpyAsync(&c->d_ctl->bad, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_dt(c, c->i0);
+    if (rc) return rc;
+    k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, c->d_tmp);
+    CU(cudaGetLastError());
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, &c->d_ctl->bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(&c->d_ctl->bad, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    *ok_out = bad ? 0 : 1;
+    return 0;
+}
+
+static int residual_common(Ctx* c, int want_grad) {
+    // one stage launch whose only target is the debug buffer (R itself)
+    StagePlan p;
+    memset(&p, 0, sizeof(p));
+    p.cur = c->i0; p.next = c->i0; p.u0 = c->i0;
+    p.ntargets = 1;
+    p.t[0].dst = 2;
+    int rc = set_active(c, 1);
+    if (rc) return rc;
+    return launch_stage(c, p, want_grad);
+}
+
+int pyh_residual(void* ctx, int gid, double* aos_out) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!aos_out) return set_err(PYH_ERR_INVALID, "null pointer");
+    int rc = residual_common(c, 0);
+    if (rc) return rc;
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    if ((rc = ensure_scratch(c, 4 * n * sizeof(double)))) return rc;
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.dbg, c->d_scratch, 4);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(aos_out, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pyh_debug_fetch(void* ctx, int gid, int what, double* aos_out) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (what < 0 || what > 2 || !aos_out) return set_err(PYH_ERR_INVALID, "bad selector / null pointer");
+    int rc;
+    bool changed = false;
+    for (auto& b : c->blocks) {
+        if (!b.dev.dbgG) {
+            void* q;
+            CU(cudaMalloc(&q, 12 * (size_t)c->lay.plane * sizeof(double)));
+            CU(cudaMemset(q, 0, 12 * (size_t)c->lay.plane * sizeof(double)));
+            b.dev.dbgG = (double*)q;
+            changed = true;
+        }
+    }
+    if (changed) {
+        std::vector<BlkDev> tmp;
+        for (auto& b : c->blocks) tmp.push_back(b.dev);
+        CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
+    }
+    if ((rc = residual_common(c, 1))) return rc;
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    if ((rc = ensure_scratch(c, 4 * n * sizeof(double)))) return rc;
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.dbgG + 4 * (size_t)what * c->lay.plane, c->d_scratch, 4);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(aos_out, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pyh_launch_count(void* ctx, int64_t* n) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !n) return set_err(PYH_ERR_INVALID, "null argument");
+    *n = c->launches;
+    return 0;
+}
+
+int pyh_stream(void* ctx, uint64_t* out) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !out) return set_err(PYH_ERR_INVALID, "null argument");
+    *out = (uint64_t)(uintptr_t)c->stream;
+    return 0;
+}
+
+int pyh_sync(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return set_err(PYH_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // extern "C"

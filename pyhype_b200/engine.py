@@ -1,0 +1,214 @@
+"""Thin Python owner of one ``pyh_ctx`` (one GPU).  Host-side plumbing only: every number is
+produced by the CUDA library behind ``include/pyh_b200.h``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PYH_MAX_STAGES, PyhBlockDesc, PyhConfig, c_double_p, check
+
+FLUX_IDS = {"Roe": 0, "HLLE": 1, "HLLL": 2}
+LIMITER_IDS = {"Venkatakrishnan": 0, "VanLeer": 1, "VanAlbada": 2, "BarthJespersen": 3}
+RECON_IDS = {"conservative": 0, "primitive": 1}
+BC_IDS = {None: 0, "Reflection": 1, "Slipwall": 2, "OutletDirichlet": 3}
+BC_DIRICHLET = 4
+SIDES = ("E", "W", "N", "S")  # SidePropertyDict order (pyhype/utils/utils.py:229-237)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    def __init__(self, nx, ny, flux, limiter, recon, tableau, gamma, cfl, device=0, num_quadrature_points=1):
+        self.lib = _lib.load()
+        if flux not in FLUX_IDS:
+            raise ValueError("Flux function type not specified.")
+        if limiter not in LIMITER_IDS:
+            raise ValueError("Slope limiter type not specified.")
+        cfg = PyhConfig()
+        cfg.abi_version = _lib.PYH_ABI_VERSION
+        cfg.device = int(device)
+        cfg.nx, cfg.ny = int(nx), int(ny)
+        cfg.flux = FLUX_IDS[flux]
+        cfg.limiter = LIMITER_IDS[limiter]
+        cfg.recon = RECON_IDS[recon]
+        cfg.num_quadrature_points = int(num_quadrature_points)
+        cfg.num_stages = len(tableau)
+        if not 1 <= len(tableau) <= PYH_MAX_STAGES:
+            raise ValueError(f"Butcher tableau must have 1..{PYH_MAX_STAGES} stages")
+        for s, row in enumerate(tableau):
+            for k, a in enumerate(row):
+                cfg.tableau[s * PYH_MAX_STAGES + k] = float(a)
+        cfg.gamma = float(gamma)
+        cfg.cfl = float(cfl)
+        self.nx, self.ny, self.num_stages = int(nx), int(ny), len(tableau)
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        check(self.lib.pyh_create(C.byref(cfg), C.byref(self._ctx)))
+        self.gids = []
+
+    # -- construction ---------------------------------------------------------------------------
+    def add_block(self, gid, mesh, neighbors, bcs, local_gids=None, is_cartesian=None):
+        """``mesh``: pyhype_b200.mesh.quad_mesh.QuadMesh; ``neighbors``/``bcs``: dicts keyed E,W,N,S.
+        A bc value is None, a string, or an (edge_len, 4) non-dimensional primitive array."""
+        d = PyhBlockDesc()
+        d.gid = int(gid)
+        d.is_cartesian = int(mesh.is_cartesian if is_cartesian is None else is_cartesian)
+        keep = []
+        for s, side in enumerate(SIDES):
+            nb = neighbors.get(side)
+            d.neighbor[s] = -1 if nb is None else int(nb)
+            d.neighbor_is_local[s] = int(nb is not None and (local_gids is None or nb in local_gids))
+            bc = bcs.get(side)
+            if isinstance(bc, np.ndarray):
+                n = self.ny if side in ("E", "W") else self.nx
+                arr = _c(bc).reshape(-1, 4)
+                if arr.shape[0] != n:
+                    raise ValueError(
+                        f"States must have equal shape, but the ghost strip has {n} cells and the inlet state {arr.shape[0]}"
+                    )
+                keep.append(arr)
+                d.bc[s] = BC_DIRICHLET
+                d.dirichlet_prim[s] = _dp(arr)
+            elif bc in BC_IDS:
+                d.bc[s] = BC_IDS[bc]
+            else:
+                raise ValueError("Boundary Condition type " + str(bc) + " has not been specialized.")
+        arrs = dict(
+            nodes_x=_c(mesh.nodes_x), nodes_y=_c(mesh.nodes_y), area=_c(mesh.area),
+            cos_v=_c(mesh.cos_v), sin_v=_c(mesh.sin_v), cos_h=_c(mesh.cos_h), sin_h=_c(mesh.sin_h),
+        )
+        assert arrs["nodes_x"].shape == (self.ny + 1, self.nx + 1)
+        assert arrs["area"].shape == (self.ny, self.nx)
+        assert arrs["cos_v"].shape == (self.ny, self.nx + 1) and arrs["cos_h"].shape == (self.ny + 1, self.nx)
+        for k, a in arrs.items():
+            setattr(d, k, _dp(a))
+        check(self.lib.pyh_add_block(self._ctx, C.byref(d)))
+        self.gids.append(int(gid))
+
+    def finalize(self):
+        check(self.lib.pyh_finalize(self._ctx))
+
+    def close(self):
+        if self._ctx:
+            self.lib.pyh_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ----------------------------------------------------------------------------------------
+    def upload(self, gid, aos):
+        a = _c(aos)
+        if a.shape != (self.ny, self.nx, 4):
+            raise ValueError(f"state must have shape {(self.ny, self.nx, 4)}, got {a.shape}")
+        check(self.lib.pyh_upload_state(self._ctx, int(gid), _dp(a)))
+
+    def download(self, gid):
+        out = np.empty((self.ny, self.nx, 4))
+        check(self.lib.pyh_download_state(self._ctx, int(gid), _dp(out)))
+        return out
+
+    def download_ghost(self, gid, side):
+        s = SIDES.index(side)
+        shape = (self.ny, 1, 4) if side in ("E", "W") else (1, self.nx, 4)
+        out = np.empty(shape)
+        check(self.lib.pyh_download_ghost(self._ctx, int(gid), s, _dp(out)))
+        return out
+
+    # -- hot path --------------------------------------------------------------------------------------
+    def apply_bc(self):
+        check(self.lib.pyh_apply_bc(self._ctx))
+
+    def get_dt(self, t, t_final):
+        dt = C.c_double()
+        check(self.lib.pyh_get_dt(self._ctx, float(t), float(t_final), C.byref(dt)))
+        return dt.value
+
+    def local_dt(self, dev_ptr):
+        check(self.lib.pyh_local_dt(self._ctx, C.c_void_p(dev_ptr)))
+
+    def step(self, dt):
+        check(self.lib.pyh_step(self._ctx, float(dt)))
+
+    def step_begin(self, dt):
+        check(self.lib.pyh_step_begin(self._ctx, float(dt)))
+
+    def step_begin_dev(self, dev_ptr):
+        check(self.lib.pyh_step_begin_dev(self._ctx, C.c_void_p(dev_ptr)))
+
+    def stage(self, s):
+        check(self.lib.pyh_stage(self._ctx, int(s)))
+
+    def run(self, t, t_final, max_steps=-1, poll_every=64, record_dts=0):
+        """Device-resident time loop; returns (t, steps_done, unrealizable, dts)."""
+        tt = C.c_double(float(t))
+        steps = C.c_int64(0)
+        bad = C.c_int32(0)
+        dts = np.zeros(max(int(record_dts), 1))
+        check(
+            self.lib.pyh_run(
+                self._ctx, C.byref(tt), float(t_final), int(max_steps), int(poll_every), C.byref(steps),
+                C.byref(bad), _dp(dts), int(record_dts),
+            )
+        )
+        n = min(steps.value, int(record_dts))
+        return tt.value, steps.value, bool(bad.value), dts[:n].copy()
+
+    def realizable(self):
+        ok = C.c_int32(0)
+        check(self.lib.pyh_realizable(self._ctx, C.byref(ok)))
+        return bool(ok.value)
+
+    # -- remote halo ------------------------------------------------------------------------------------
+    def halo_slots(self):
+        n = C.c_int64()
+        nd = C.c_int64()
+        check(self.lib.pyh_halo_count(self._ctx, C.byref(n), C.byref(nd)))
+        out = []
+        for s in range(n.value):
+            gid, side, nbr = C.c_int32(), C.c_int32(), C.c_int32()
+            off, ln = C.c_int64(), C.c_int64()
+            check(self.lib.pyh_halo_slot(self._ctx, s, C.byref(gid), C.byref(side), C.byref(nbr), C.byref(off), C.byref(ln)))
+            out.append(dict(gid=gid.value, side=SIDES[side.value], nbr=nbr.value, offset=off.value, length=ln.value))
+        return out, nd.value
+
+    def pack_halo(self, dev_ptr):
+        check(self.lib.pyh_pack_halo(self._ctx, C.c_void_p(dev_ptr)))
+
+    def unpack_halo(self, dev_ptr):
+        check(self.lib.pyh_unpack_halo(self._ctx, C.c_void_p(dev_ptr)))
+
+    # -- test hooks / counters ---------------------------------------------------------------------------
+    def residual(self, gid):
+        out = np.empty((self.ny, self.nx, 4))
+        check(self.lib.pyh_residual(self._ctx, int(gid), _dp(out)))
+        return out
+
+    def debug_fetch(self, gid, what):
+        out = np.empty((self.ny, self.nx, 4))
+        check(self.lib.pyh_debug_fetch(self._ctx, int(gid), {"gx": 0, "gy": 1, "phi": 2}[what], _dp(out)))
+        return out
+
+    def launch_count(self):
+        n = C.c_int64()
+        check(self.lib.pyh_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        s = C.c_uint64()
+        check(self.lib.pyh_stream(self._ctx, C.byref(s)))
+        return s.value
+
+    def sync(self):
+        check(self.lib.pyh_sync(self._ctx))

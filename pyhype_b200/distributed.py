@@ -1,0 +1,106 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink) as transport.
+
+Replaces the reference's mpi4py layer (pyhype/blocks/ghost.py:169-241 Isend/Irecv per ghost
+strip, pyhype/blocks/base.py:454-465 Waitall, pyhype/solvers/base.py:128-131 gather+bcast of dt):
+
+* blocks are dealt to ranks with the reference's contiguous rule
+  (``Blocks.distribute_blocks_to_processes``, pyhype/blocks/base.py:473-513);
+* per RK stage every rank packs the edge strips its remote neighbours need into one device
+  buffer (``pyh_pack_halo``), exchanges them with grouped send/recv, and unpacks the received
+  strips into its ghost frames (``pyh_unpack_halo``); same-rank edges never leave the device;
+* the global CFL step is ``all_reduce(MIN)`` on one fp64 device scalar (min is exact, so the
+  result does not depend on the rank count).
+
+The sharded result is bit-identical to the single-GPU one: every residual reads only the
+block's own cells and its ghost frame, which holds the same values either way.
+"""
+from __future__ import annotations
+
+import os
+
+OPPOSITE = {"E": "W", "W": "E", "N": "S", "S": "N"}
+
+
+def distribute_blocks(num_blocks: int, num_processes: int) -> dict:
+    """{block_num: rank}; the first ``num_blocks % num_processes`` ranks get one extra block
+    (pyhype/blocks/base.py:473-513)."""
+    owner = {}
+    counter = 0
+    full = num_blocks % num_processes
+    base = num_blocks // num_processes
+    for r in range(num_processes):
+        n = base + 1 if r < full else base
+        for g in range(counter, counter + n):
+            owner[g] = r
+        counter += n
+    return owner
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process per GPU)."""
+    return (
+        int(os.environ.get("RANK", "0")),
+        int(os.environ.get("WORLD_SIZE", "1")),
+        int(os.environ.get("LOCAL_RANK", "0")),
+    )
+
+
+def exchange_plan(slots, owner, rank):
+    """Order the point-to-point messages of one stage.
+
+    ``slots``: this rank's halo slots from ``Engine.halo_slots()``.  Returns two lists of
+    (peer, key, offset, length): sends and receives, each sorted by (peer, key) where the key
+    (source block, source side) names a message uniquely on both ends, so the k-th send of
+    rank a to rank b meets the k-th receive b posts for a.
+    """
+    sides = ("E", "W", "N", "S")
+    sends, recvs = [], []
+    for s in slots:
+        peer = owner[s["nbr"]]
+        if peer == rank:
+            raise ValueError("halo slot whose neighbour is local")
+        sends.append((peer, (s["gid"], sides.index(s["side"])), s["offset"], s["length"]))
+        recvs.append((peer, (s["nbr"], sides.index(OPPOSITE[s["side"]])), s["offset"], s["length"]))
+    sends.sort(key=lambda m: (m[0], m[1]))
+    recvs.sort(key=lambda m: (m[0], m[1]))
+    return sends, recvs
+
+
+class HaloExchanger:
+    """Owns the send/recv device buffers of one engine and runs the per-stage exchange."""
+
+    def __init__(self, engine, owner, rank, group=None, backend_device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.engine = engine
+        self.group = group
+        slots, ndoubles = engine.halo_slots()
+        self.sends, self.recvs = exchange_plan(slots, owner, rank)
+        dev = backend_device if backend_device is not None else torch.device("cuda", engine.device)
+        self.sendbuf = torch.zeros(max(ndoubles, 1), dtype=torch.float64, device=dev)
+        self.recvbuf = torch.zeros(max(ndoubles, 1), dtype=torch.float64, device=dev)
+        self.empty = ndoubles == 0
+        self.dt = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def exchange(self):
+        """pack -> grouped isend/irecv -> unpack (all on the current torch stream)."""
+        if self.empty:
+            return
+        dist = self.dist
+        self.engine.pack_halo(self.sendbuf.data_ptr())
+        ops = []
+        for peer, _k, off, ln in self.recvs:
+            ops.append(dist.P2POp(dist.irecv, self.recvbuf[off:off + ln], peer, group=self.group))
+        for peer, _k, off, ln in self.sends:
+            ops.append(dist.P2POp(dist.isend, self.sendbuf[off:off + ln], peer, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.engine.unpack_halo(self.recvbuf.data_ptr())
+
+    def global_dt(self):
+        """CFL * global min, left on the device (solvers/base.py:126-131)."""
+        self.engine.local_dt(self.dt.data_ptr())
+        self.dist.all_reduce(self.dt, op=self.dist.ReduceOp.MIN, group=self.group)
+        return self.dt

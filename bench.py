@@ -128,7 +128,7 @@ class ClockSampler:
 def run_ours(args):
     import torch
 
-    from pyhype_b200.distributed import HaloExchanger, distribute_blocks, world
+    from pyhype_b200.distributed import HaloExchanger, advance, distribute_blocks, world
     from pyhype_b200.engine import Engine, SIDES
     from pyhype_b200.mesh.quad_mesh import QuadMesh
     from pyhype_b200.time_marching import get_tableau
@@ -184,14 +184,11 @@ def run_ours(args):
     def one_step():
         """get_dt + integrate (Euler2D._solve body, pyhype/solvers/Euler2D.py:199-204), dt stays on the device"""
         if hx is not None:
-            dt = hx.global_dt()
-            eng.step_begin_dev(dt.data_ptr())
+            ptr = hx.global_dt().data_ptr()
         else:
             eng.local_dt(dt_dev.data_ptr())
-            eng.step_begin_dev(dt_dev.data_ptr())
-        for s in range(nstages):
-            eng.stage(s)
-            refresh_ghosts()
+            ptr = dt_dev.data_ptr()
+        advance(eng, hx, nstages, dt_dev_ptr=ptr)
 
     def barrier():
         if dist is not None:

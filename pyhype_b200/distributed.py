@@ -104,3 +104,18 @@ class HaloExchanger:
         self.engine.local_dt(self.dt.data_ptr())
         self.dist.all_reduce(self.dt, op=self.dist.ReduceOp.MIN, group=self.group)
         return self.dt
+
+
+def advance(engine, halo, num_stages, dt=None, dt_dev_ptr=None):
+    """One time step of ExplicitRungeKutta.integrate (explicit_runge_kutta.py:63-80) on a sharded
+    domain: per stage the fused stage kernel, then the remote strip exchange, then the local ghost
+    copies + BC functors (Blocks.apply_boundary_condition, blocks/base.py:448-471)."""
+    if dt_dev_ptr is not None:
+        engine.step_begin_dev(dt_dev_ptr)
+    else:
+        engine.step_begin(dt)
+    for s in range(num_stages):
+        engine.stage(s)
+        if halo is not None:
+            halo.exchange()
+        engine.apply_bc()

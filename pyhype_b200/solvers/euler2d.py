@@ -1,0 +1,315 @@
+"""Euler2D -- the drop-in seam.  Same constructor, attributes and ``solve()`` as
+``pyhype.solvers.Euler2D`` (pyhype/solvers/Euler2D.py:45-216, pyhype/solvers/base.py:40-172); the
+three calls its time loop makes per step (``get_dt``, ``integrate``, realizability check) and the
+ghost refresh run on the GPU through the C ABI of ``include/pyh_b200.h``."""
+from __future__ import annotations
+
+import logging
+import pathlib
+from datetime import datetime
+
+import numpy as np
+
+from ..blocks import SIDES, QuadBlock
+from ..boundary_conditions.base import BoundaryCondition, PrimitiveDirichletBC
+from ..distributed import advance, distribute_blocks, world
+from ..engine import FLUX_IDS, LIMITER_IDS, Engine
+from ..mesh.base import MeshGenerator
+from ..states import ConservativeState, PrimitiveState, RealizabilityException
+from ..time_marching import get_tableau
+
+
+class _Logger:
+    def __init__(self, config, rank):
+        self._log = logging.getLogger("pyhype_b200")
+        procs = config.show_log_for_procs
+        self._on = procs == "all" or rank in procs
+
+    def info(self, msg):
+        if self._on:
+            self._log.info(msg)
+
+    def error(self, msg):
+        self._log.error(msg)
+
+
+def _validate(config):
+    """Reject what the reference rejects, with the same exception types."""
+    if config.fvm_type != "MUSCL":
+        raise ValueError("Specified finite volume method has not been specialized.")
+    if config.fvm_spatial_order != 2:
+        # order 1 never reaches the FVM in the reference: GradientsFactory only knows orders 2 and 4
+        # (pyhype/blocks/base.py:369-376)
+        raise ValueError(
+            "GradientsFactory.create_gradients(): Error, no gradients container class has been "
+            "extended for the given order."
+        )
+    if config.nghost != 1:
+        raise ValueError("Number of ghost cells must be equal to 1 for this method.")  # SecondOrderMUSCL.py:49-52
+    if config.fvm_gradient_type != "GreenGauss":
+        raise ValueError("Gradient type not specified.")
+    if config.fvm_flux_function_type not in FLUX_IDS:
+        raise ValueError("Flux function type not specified.")
+    if config.fvm_slope_limiter_type not in LIMITER_IDS:
+        raise ValueError("Slope limiter type not specified.")
+    if config.interface_interpolation != "arithmetic_average":
+        raise ValueError("Interface Interpolation method is not defined.")  # quad_block.py:144-152
+    if config.reconstruction_type not in (ConservativeState, PrimitiveState):
+        raise ValueError("reconstruction_type must be ConservativeState or PrimitiveState")
+    if config.fvm_num_quadrature_points not in (1, 2, 3):
+        raise KeyError(config.fvm_num_quadrature_points)
+    if config.fvm_num_quadrature_points != 1:
+        raise NotImplementedError(
+            "pyhype_b200: only fvm_num_quadrature_points == 1 is implemented on the GPU path (DESIGN.md, next)"
+        )
+
+
+class Euler2D:
+    def __init__(self, config, mesh_config, device=None) -> None:
+        self.config = config
+        self.fluid = config.fluid
+        self.cpu, self._world, local_rank = world()
+        self._logger = _Logger(config, self.cpu)
+        _validate(config)
+        tableau = get_tableau(config.time_integrator)
+        mesh_info = mesh_config.dict if isinstance(mesh_config, MeshGenerator) else mesh_config
+        self.mesh_config = mesh_info
+
+        self.t = 0
+        self.num_time_step = 0
+        self.CFL = config.CFL
+        self.t_final = config.t_final * self.fluid.far_field.a  # solvers/base.py:73
+        self.profile_data = None
+        self.write_path = None
+        if config.write_solution:
+            self.write_path = pathlib.Path(config.write_solution_base) / config.write_solution_name
+            if self.cpu == 0:
+                self.write_path.mkdir(exist_ok=True, parents=True)
+
+        # block -> rank map; block ids must be 0..N-1 (pyhype/blocks/base.py:515-534)
+        owner = distribute_blocks(len(mesh_info), self._world)
+        mine = [g for g, r in owner.items() if r == self.cpu]
+        self._owner = owner
+        self._blocks = {}
+        for g in mine:
+            self._blocks[g] = QuadBlock(config, mesh_info[g], self)  # KeyError like the reference if ids are not 0..N-1
+
+        recon = "primitive" if config.reconstruction_type is PrimitiveState else "conservative"
+        self._device = local_rank if device is None else device
+        self._engine = Engine(
+            config.nx, config.ny, config.fvm_flux_function_type, config.fvm_slope_limiter_type, recon, tableau,
+            self.fluid.gamma(), config.CFL, device=self._device,
+            num_quadrature_points=config.fvm_num_quadrature_points,
+        )
+        local = set(mine)
+        for g, blk in self._blocks.items():
+            bcs = {}
+            for s in SIDES:
+                bc = blk.info.bc[s]
+                if isinstance(bc, PrimitiveDirichletBC):
+                    inlet = bc.primitive_state.data
+                    want = (config.ny, 1, 4) if s in ("E", "W") else (1, config.nx, 4)
+                    if inlet.shape != want:  # states/converter/state_converter.py:60-63
+                        raise ValueError(
+                            f"States must have equal shape, but state has {want} and from_state has {inlet.shape}"
+                        )
+                    bcs[s] = np.ascontiguousarray(inlet, dtype=np.float64)
+                elif isinstance(bc, BoundaryCondition):
+                    raise ValueError("Boundary Condition type " + str(bc) + " has not been specialized.")
+                else:
+                    bcs[s] = bc
+            self._engine.add_block(g, blk.mesh, blk.info.neighbors, bcs, local_gids=local)
+            blk._attach(self._engine)
+        self._engine.finalize()
+        self._halo = None
+        if self._world > 1:
+            import torch
+            import torch.distributed as dist
+
+            from ..distributed import HaloExchanger
+
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self._device))
+            self._torch = torch
+            self._stream = torch.cuda.ExternalStream(self._engine.stream(), device=torch.device("cuda", self._device))
+            with torch.cuda.stream(self._stream):
+                self._halo = HaloExchanger(self._engine, owner, self.cpu)
+        self._logger.info("\n\tFinished setting up solver")
+
+    def __str__(self):
+        c = self.config
+        return (
+            "\tA Solver of type Euler2D for solving the 2D Euler\n\tequations on structured grids using the Finite Volume Method.\n\n"
+            f"\t{'Finite Volume Method: ':<40} {c.fvm_type}\n\t{'Gradient Method: ':<40} {c.fvm_gradient_type}\n"
+            f"\t{'Flux Function: ':<40} {c.fvm_flux_function_type}\n\t{'Limiter: ':<40} {c.fvm_slope_limiter_type}\n"
+            f"\t{'Time Integrator: ':<40} {c.time_integrator}"
+        )
+
+    # -- reference surface -----------------------------------------------------------------------------
+    @property
+    def blocks(self):
+        return self._blocks.values()
+
+    def apply_initial_condition(self):
+        for block in self.blocks:
+            self.config.initial_condition.apply_to_block(block)
+
+    def apply_boundary_condition(self):
+        self._flush_host_states()
+        self._refresh_ghosts()
+
+    def get_dt(self) -> float:
+        """solvers/base.py:114-136"""
+        self._flush_host_states()
+        if self._halo is None:
+            return self._engine.get_dt(self.t, self.t_final)
+        with self._torch.cuda.stream(self._stream):
+            dt = float(self._halo.global_dt().item())
+        return self.t_final - self.t if self.t_final - self.t < dt else dt
+
+    def solve(self):
+        self._pre_process_solve()
+        self._solve()
+        self._post_process_solve()
+
+    # -- internals ---------------------------------------------------------------------------------------
+    def _flush_host_states(self):
+        for block in self.blocks:
+            block.state.push_if_touched()
+
+    def _mark_device_newer(self):
+        for block in self.blocks:
+            block.state.mark_device_newer()
+
+    def _refresh_ghosts(self):
+        if self._halo is not None:
+            with self._torch.cuda.stream(self._stream):
+                self._halo.exchange()
+                self._engine.apply_bc()
+        else:
+            self._engine.apply_bc()
+
+    def _pre_process_solve(self):
+        self._logger.info("\t>>> Setting Initial Conditions")
+        self.apply_initial_condition()
+        self._logger.info("\t>>> Setting Boundary Conditions")
+        self.apply_boundary_condition()
+        if self.config.realplot:
+            self._logger.info("\t>>> realplot is not available on the GPU path (matplotlib-free); ignored")
+        if self.config.write_solution:
+            self.write_mesh()
+        self._logger.info(f"Date and time: {datetime.today()}")
+
+    def _post_process_solve(self):
+        self._logger.info(
+            f"Simulation time: {str(self.t / self.fluid.far_field.a)}, Timestep number: {str(self.num_time_step)}"
+        )
+        self._logger.info("End of simulation")
+
+    def _update_solution_blocks(self, dt: float) -> None:
+        """ExplicitRungeKutta.integrate (time_marching/explicit_runge_kutta.py:47-80)"""
+        self._flush_host_states()
+        if self._halo is None:
+            self._engine.step(dt)
+        else:
+            with self._torch.cuda.stream(self._stream):
+                advance(self._engine, self._halo, self._engine.num_stages, dt=dt)
+        self._mark_device_newer()
+
+    def _realizability_check(self):
+        ok = self._engine.realizable()
+        if self._halo is not None:
+            flag = self._torch.tensor([0 if ok else 1], device=f"cuda:{self._device}")
+            self._torch.distributed.all_reduce(flag)
+            ok = int(flag.item()) == 0
+        if not ok:
+            msg = "ConservativeState has unrealizable values (rho <= 0 or e <= 0)"
+            self._logger.error(msg)
+            raise RealizabilityException(msg)  # the reference logs and calls MPI.Abort (Euler2D.py:144-152)
+
+    def step(self):
+        """One pass of the loop body of Euler2D._solve (Euler2D.py:199-210)."""
+        dt = self.get_dt()
+        self._update_solution_blocks(dt)
+        self._realizability_check()
+        if self.config.write_solution:
+            self.write_solution()
+        self.t += dt
+        self.num_time_step += 1
+        return dt
+
+    def _solve(self) -> None:
+        profiler = None
+        if self.config.profile:
+            import cProfile
+
+            profiler = cProfile.Profile()
+            profiler.enable()
+        writes = self.config.write_solution and self.config.write_solution_mode == "every_n_timesteps"
+        if self._halo is not None:
+            while self.t < self.t_final:
+                if self.num_time_step % 50 == 0:
+                    self._log_progress()
+                self.step()
+        else:
+            # device-resident loop between output points: dt, t and the step counter stay on the GPU
+            self._flush_host_states()
+            while self.t < self.t_final:
+                self._log_progress()
+                if writes:
+                    every = self.config.write_every_n_timesteps
+                    nxt = (every - self.num_time_step % every) + 1 if self.num_time_step % every else 1
+                else:
+                    nxt = -1
+                # the reference writes *after* the update of a step whose counter is a multiple of
+                # `every`, before the counter is incremented (Euler2D.py:206-210)
+                t, n, bad, _ = self._engine.run(self.t, self.t_final, max_steps=nxt, poll_every=50)
+                self._mark_device_newer()
+                if bad:
+                    msg = "ConservativeState has unrealizable values (rho <= 0 or e <= 0)"
+                    self._logger.error(msg)
+                    raise RealizabilityException(msg)
+                if n == 0:
+                    break
+                self.num_time_step += n - 1
+                if writes:
+                    self.write_solution()
+                self.num_time_step += 1
+                self.t = t
+        if profiler is not None:
+            import pstats
+
+            profiler.disable()
+            self.profile_data = pstats.Stats(profiler)
+            if self.cpu == 0:
+                self.profile_data.sort_stats("tottime").print_stats(50)
+
+    def _log_progress(self):
+        self._logger.info(
+            f"Simulation time: {self.t / self.fluid.far_field.a}, Timestep number: {self.num_time_step}"
+        )
+
+    # -- npy output, same layout as the reference (solvers/base.py:142-172) ---------------------------------
+    @staticmethod
+    def write_output_nodes(filename: str, array: np.ndarray):
+        np.save(file=filename, arr=array)
+
+    def write_mesh(self):
+        current_path = self.write_path / "mesh"
+        current_path.mkdir(parents=True, exist_ok=True)
+        for block in self.blocks:
+            self.write_output_nodes(str(current_path / "mesh_x_blk_") + str(block.global_block_num), block.mesh.x)
+            self.write_output_nodes(str(current_path / "mesh_y_blk_") + str(block.global_block_num), block.mesh.y)
+
+    def write_solution(self):
+        if (
+            self.config.write_solution_mode == "every_n_timesteps"
+            and self.num_time_step % self.config.write_every_n_timesteps == 0
+        ):
+            current_path = self.write_path / str(self.num_time_step)
+            current_path.mkdir(parents=True, exist_ok=True)
+            for block in self.blocks:
+                self.write_output_nodes(
+                    str(current_path / self.config.write_solution_name) + "_blk_" + str(block.global_block_num),
+                    block.state.data,
+                )

@@ -1,0 +1,77 @@
+"""Pins the oracle against the LIVE reference when /root/reference is present (build container
+only; skipped on the GPU box, where the committed fixtures under tests/golden/ take over)."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import muscl_oracle as mo
+from oracle import refharness as rh
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="reference tree not present")
+
+
+def _compare(blocks, nx, ny, ic, nsteps, **cfg):
+    from make_golden import ref_blocks  # noqa: F401  (same adaptor the fixtures were made with)
+
+    class IC:
+        def apply_to_block(self, block):
+            block.state.data = np.ascontiguousarray(ic(block.mesh.x[:, :, 0], block.mesh.y[:, :, 0]))
+
+    config = rh.make_config(nx=nx, ny=ny, initial_condition=IC(), **cfg)
+    run = rh.RefRun(config, ref_blocks(blocks))
+    recon = cfg.get("reconstruction_type", "conservative")
+    prob = mo.Problem(blocks, nx, ny, flux=config.fvm_flux_function_type, limiter=config.fvm_slope_limiter_type,
+                      recon=recon, integrator=config.time_integrator, CFL=config.CFL, nqp=config.fvm_num_quadrature_points)
+    for b, rb in zip(prob.blocks.values(), run.blocks):
+        b.U = rb.state.data.copy()
+    prob.apply_bc()
+    for b, r in zip(prob.blocks.values(), run.residuals()):
+        prob.residual(b, keep=True)
+        for k in ("gx", "gy", "phi", "FE", "FW", "FN", "FS", "R"):
+            assert np.array_equal(b.dbg[k], r[k]), (b.gid, k)
+    run.step(nsteps)
+    _, dts = prob.run(0.0, config.t_final * 343.0, max_steps=nsteps)
+    assert dts == run.dts
+    for b, rb, gh in zip(prob.blocks.values(), run.blocks, run.ghosts()):
+        assert np.array_equal(b.U, rb.state.data)
+        for s in ("E", "W", "N", "S"):
+            assert np.array_equal(b.ghost[s], gh[s])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _path():
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    rh.activate()
+    yield
+
+
+def test_live_explosion_multi_roe_rk4():
+    _compare(cases.em_mesh(), 20, 20, cases.explosion_ic, 6)
+
+
+def test_live_dmr_hlll_primitive_rk2():
+    _compare(cases.dmr_mesh(), 20, 20, cases.dmr_ic, 8, fvm_flux_function_type="HLLL", time_integrator="RK2",
+             CFL=0.4, reconstruction_type="primitive")
+
+
+def test_live_wedge_dirichlet():
+    _compare(cases.wedge_mesh(12), 14, 12, cases.wedge_ic, 8, fvm_flux_function_type="HLLL", time_integrator="RK2",
+             CFL=0.3, reconstruction_type="primitive")
+
+
+def test_live_nrm2_matches_numba_linalg_norm():
+    import numba as nb
+
+    @nb.njit
+    def norms(v):
+        out = np.zeros(v.shape[0])
+        for i in range(v.shape[0]):
+            out[i] = np.linalg.norm(v[i])
+        return out
+
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((50000, 4)) * 10.0 ** rng.integers(-8, 8, size=(50000, 1))
+    assert np.array_equal(norms(v), mo.nrm2_x87(v))

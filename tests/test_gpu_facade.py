@@ -98,7 +98,7 @@ def test_manual_stepping_and_lazy_state_sync():
 
 
 def test_write_solution_layout(tmp_path):
-    config = em_config(nx=12, ny=12, t_final=0.0015, write_solution=True, write_solution_mode="every_n_timesteps",
+    config = em_config(nx=12, ny=12, t_final=0.005, write_solution=True, write_solution_mode="every_n_timesteps",
                        write_solution_name="explosion_multi", write_solution_base=str(tmp_path), write_every_n_timesteps=3)
     sim = Euler2D(config=config, mesh_config=em_mesh())
     sim.solve()

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "pyh_kernels.cuh"
+#include "pyh_stage_march.cuh"
 
 using namespace pyh;
 
@@ -61,7 +62,8 @@ struct Ctx {
     double* d_dts = nullptr;
     long long dts_cap = 0;
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
-    int tile_kind = 0;
+    int stage_kernel = 1;          // 0: shared-memory tile kernel, 1: row-marching kernel (PYH_STAGE_KERNEL)
+    int march_nt = 128, march_tys = 64;
 };
 
 int ensure_scratch(Ctx* c, size_t bytes) {
@@ -115,7 +117,10 @@ StageFn pick_stage(int f, int l, int p) {
     }
 }
 
+int launch_stage_march(Ctx* c, const StagePlan& plan, int want_grad_dbg);
+
 int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
+    if (c->stage_kernel == 1) return launch_stage_march(c, plan, want_grad_dbg);
     StageFn fn = pick_stage(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
     size_t smem = TileShape<TX, TY>::SMEM_DOUBLES * sizeof(double);
     static thread_local StageFn configured[64];
@@ -128,6 +133,62 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
     }
     dim3 grid(cdiv(c->lay.nx, TX), cdiv(c->lay.ny, TY), (unsigned)c->blocks.size());
     fn<<<grid, NT, smem, c->stream>>>(c->d_blks, c->lay, plan, c->d_ctl, c->C, want_grad_dbg);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+typedef void (*MarchFn)(const BlkDev*, Layout, StagePlan, const Control*, Consts, int, int);
+template <int F, int L>
+MarchFn mpick_p(int p) { return p ? k_stage_march<F, L, 1> : k_stage_march<F, L, 0>; }
+template <int F>
+MarchFn mpick_l(int l, int p) {
+    switch (l) {
+        case 0: return mpick_p<F, 0>(p);
+        case 1: return mpick_p<F, 1>(p);
+        case 2: return mpick_p<F, 2>(p);
+        default: return mpick_p<F, 3>(p);
+    }
+}
+MarchFn pick_march(int f, int l, int p) {
+    switch (f) {
+        case 0: return mpick_l<0>(l, p);
+        case 1: return mpick_l<1>(l, p);
+        default: return mpick_l<2>(l, p);
+    }
+}
+
+// lanes per CTA: two ring lanes per strip, so pick the width that wastes the fewest lanes for this nx
+void choose_march_shape(Ctx* c) {
+    const int cand[] = {64, 96, 128, 160, 192};
+    double best = -1.0;
+    int nt = 128;
+    for (int n : cand) {
+        if (n > MARCH_MAX_THREADS) continue;
+        int strips = (c->lay.nx + n - 3) / (n - 2);
+        double util = (double)c->lay.nx / ((double)strips * n);
+        if (util > best + 1e-9 || (util > best - 1e-9 && n > nt)) { best = util; nt = n; }
+    }
+    if (const char* e = getenv("PYH_MARCH_NT")) { int v = atoi(e); if (v >= 32 && v <= MARCH_MAX_THREADS && v % 32 == 0) nt = v; }
+    c->march_nt = nt;
+    int tys = 64;
+    if (const char* e = getenv("PYH_MARCH_TYS")) { int v = atoi(e); if (v >= 1) tys = v; }
+    // enough CTAs to fill 148 SMs a few times over
+    long long nsx = (c->lay.nx + nt - 3) / (nt - 2);
+    long long per_row_strip = nsx * (long long)std::max<size_t>(c->blocks.size(), 1);
+    long long want_nsy = (148 * 6 + per_row_strip - 1) / per_row_strip;
+    if (want_nsy < 1) want_nsy = 1;
+    int cap = (int)((c->lay.ny + want_nsy - 1) / want_nsy);
+    tys = std::max(4, std::min(tys, cap));
+    c->march_tys = tys;
+}
+
+int launch_stage_march(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
+    MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
+    const int nt = c->march_nt, tys = c->march_tys;
+    size_t smem = (size_t)16 * nt * sizeof(double);
+    dim3 grid(cdiv(c->lay.nx, nt - 2), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
+    fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, plan, c->d_ctl, c->C, tys, want_grad_dbg);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -238,6 +299,7 @@ int pyh_create(const pyh_config* cfg, void** out) {
         for (int k = 0; k < r && r < cfg->num_stages; ++k)
             if (c->tab.a[r * PYH_MAX_STAGES + k] != 0.0) c->need_acc[r] = true;
     }
+    if (const char* e = getenv("PYH_STAGE_KERNEL")) c->stage_kernel = (strcmp(e, "tile") == 0) ? 0 : 1;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
     Control h;
@@ -380,6 +442,7 @@ int pyh_finalize(void* ctx) {
         CU(cudaMalloc(&c->d_slots, c->slots.size() * sizeof(HaloSlot)));
         CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
     }
+    choose_march_shape(c);
     c->finalized = true;
     return 0;
 }

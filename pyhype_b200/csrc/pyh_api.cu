@@ -34,12 +34,13 @@ namespace {
 struct HostBlock {
     pyh_block_desc d;   // pointers inside are NOT retained
     BlkDev dev;
-    std::vector<void*> allocs;
+    std::vector<void*> allocs;   // slab + Dirichlet strips (+ on-demand debug buffers)
 };
 
 struct Ctx {
     pyh_config cfg;
     Layout lay;
+    PlaneOffsets po;
     Consts C;
     Tableau tab;
     cudaStream_t stream = nullptr;
@@ -62,7 +63,6 @@ struct Ctx {
     double* d_dts = nullptr;
     long long dts_cap = 0;
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
-    int stage_kernel = 1;          // 0: shared-memory tile kernel, 1: row-marching kernel (PYH_STAGE_KERNEL)
     int march_nt = 128, march_tys = 64;
 };
 
@@ -92,53 +92,7 @@ int dalloc(HostBlock& hb, double** p, long long ndoubles, bool zero) {
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- stage kernel dispatch ------------------------------------------------------------------------
-constexpr int TX = 32, TY = 8, NT = 256;
-typedef void (*StageFn)(const BlkDev*, Layout, StagePlan, const Control*, Consts, int);
-
-template <int F, int L, int P>
-StageFn stage_fn() { return k_stage_tile<F, L, P, TX, TY, NT>; }
-
-template <int F, int L>
-StageFn pick_p(int p) { return p ? stage_fn<F, L, 1>() : stage_fn<F, L, 0>(); }
-template <int F>
-StageFn pick_l(int l, int p) {
-    switch (l) {
-        case 0: return pick_p<F, 0>(p);
-        case 1: return pick_p<F, 1>(p);
-        case 2: return pick_p<F, 2>(p);
-        default: return pick_p<F, 3>(p);
-    }
-}
-StageFn pick_stage(int f, int l, int p) {
-    switch (f) {
-        case 0: return pick_l<0>(l, p);
-        case 1: return pick_l<1>(l, p);
-        default: return pick_l<2>(l, p);
-    }
-}
-
-int launch_stage_march(Ctx* c, const StagePlan& plan, int want_grad_dbg);
-
-int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
-    if (c->stage_kernel == 1) return launch_stage_march(c, plan, want_grad_dbg);
-    StageFn fn = pick_stage(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
-    size_t smem = TileShape<TX, TY>::SMEM_DOUBLES * sizeof(double);
-    static thread_local StageFn configured[64];
-    static thread_local int nconf = 0;
-    bool done = false;
-    for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
-    if (!done) {
-        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (nconf < 64) configured[nconf++] = fn;
-    }
-    dim3 grid(cdiv(c->lay.nx, TX), cdiv(c->lay.ny, TY), (unsigned)c->blocks.size());
-    fn<<<grid, NT, smem, c->stream>>>(c->d_blks, c->lay, plan, c->d_ctl, c->C, want_grad_dbg);
-    CU(cudaGetLastError());
-    c->launches++;
-    return 0;
-}
-
-typedef void (*MarchFn)(const BlkDev*, Layout, StagePlan, const Control*, Consts, int, int);
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int);
 template <int F, int L>
 MarchFn mpick_p(int p) { return p ? k_stage_march<F, L, 1> : k_stage_march<F, L, 0>; }
 template <int F>
@@ -165,7 +119,7 @@ void choose_march_shape(Ctx* c) {
     int nt = 128;
     for (int n : cand) {
         if (n > MARCH_MAX_THREADS) continue;
-        int strips = (c->lay.nx + n - 3) / (n - 2);
+        int strips = (c->lay.nx + n - 5) / (n - 4);
         double util = (double)c->lay.nx / ((double)strips * n);
         if (util > best + 1e-9 || (util > best - 1e-9 && n > nt)) { best = util; nt = n; }
     }
@@ -174,7 +128,7 @@ void choose_march_shape(Ctx* c) {
     int tys = 64;
     if (const char* e = getenv("PYH_MARCH_TYS")) { int v = atoi(e); if (v >= 1) tys = v; }
     // enough CTAs to fill 148 SMs a few times over
-    long long nsx = (c->lay.nx + nt - 3) / (nt - 2);
+    long long nsx = (c->lay.nx + nt - 5) / (nt - 4);
     long long per_row_strip = nsx * (long long)std::max<size_t>(c->blocks.size(), 1);
     long long want_nsy = (148 * 6 + per_row_strip - 1) / per_row_strip;
     if (want_nsy < 1) want_nsy = 1;
@@ -183,12 +137,20 @@ void choose_march_shape(Ctx* c) {
     c->march_tys = tys;
 }
 
-int launch_stage_march(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
     MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
     const int nt = c->march_nt, tys = c->march_tys;
-    size_t smem = (size_t)16 * nt * sizeof(double);
-    dim3 grid(cdiv(c->lay.nx, nt - 2), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
-    fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, plan, c->d_ctl, c->C, tys, want_grad_dbg);
+    size_t smem = (size_t)MARCH_SMEM_DOUBLES_PER_THREAD * nt * sizeof(double);
+    static thread_local MarchFn configured[64];
+    static thread_local int nconf = 0;
+    bool done = false;
+    for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
+    if (!done) {
+        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM_DOUBLES_PER_THREAD * MARCH_MAX_THREADS * (int)sizeof(double)));
+        if (nconf < 64) configured[nconf++] = fn;
+    }
+    dim3 grid(cdiv(c->lay.nx, nt - 4), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
+    fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -199,22 +161,20 @@ int launch_stage_march(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
 StagePlan make_plan(Ctx* c, int s, int cur, int next) {
     StagePlan p;
     memset(&p, 0, sizeof(p));
-    p.cur = cur; p.next = next; p.u0 = c->i0;
+    p.cur = c->po.H[cur];
     const int S = c->cfg.num_stages;
     auto a = [&](int r, int k) { return c->tab.a[r * PYH_MAX_STAGES + k]; };
     for (int r = s; r < S; ++r) {
         bool prior = false;
         for (int k = 0; k < s; ++k) if (a(r, k) != 0.0) prior = true;
         bool nz = a(r, s) != 0.0;
-        if (r == s) {
-            RkTarget t;
-            t.src = prior ? 1 : 0; t.dst = 0; t.row = r; t.add = nz ? 1 : 0; t.coef = r * PYH_MAX_STAGES + s;
-            p.t[p.ntargets++] = t;
-        } else if (nz) {
-            RkTarget t;
-            t.src = prior ? 1 : 0; t.dst = 1; t.row = r; t.add = 1; t.coef = r * PYH_MAX_STAGES + s;
-            p.t[p.ntargets++] = t;
-        }
+        if (r != s && !nz) continue;
+        RkTarget t;
+        t.src = prior ? c->po.P[r] : c->po.H[c->i0];
+        t.dst = (r == s) ? c->po.H[next] : c->po.P[r];
+        t.add = nz ? 1 : 0;
+        t.coef = r * PYH_MAX_STAGES + s;
+        p.t[p.ntargets++] = t;
     }
     return p;
 }
@@ -222,7 +182,7 @@ StagePlan make_plan(Ctx* c, int s, int cur, int next) {
 int do_ghost(Ctx* c, int buf) {
     int m = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(m, 128), 4, (unsigned)c->blocks.size());
-    k_ghost<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, buf, c->d_ctl);
+    k_ghost<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po, c->po.H[buf], c->d_ctl);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -253,7 +213,7 @@ int set_active(Ctx* c, int active) {
 int launch_dt(Ctx* c, int buf, int respect_active = 0) {
     long long total = (long long)c->lay.nx * c->lay.ny * (long long)c->blocks.size();
     int grid = (int)std::min<long long>(cdiv(total, 256), 148 * 8);
-    k_dt<<<grid, 256, 0, c->stream>>>(c->d_blks, c->lay, buf, (int)c->blocks.size(), c->d_ctl, c->C, respect_active);
+    k_dt<<<grid, 256, 0, c->stream>>>(c->d_blks, c->lay, c->po, c->po.H[buf], (int)c->blocks.size(), c->d_ctl, c->C, respect_active);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -285,7 +245,11 @@ int pyh_create(const pyh_config* cfg, void** out) {
     c->cfg = *cfg;
     c->lay.nx = cfg->nx; c->lay.ny = cfg->ny;
     c->lay.pitch = ((cfg->nx + PADL + 1 + 3) / 4) * 4;
-    c->lay.plane = (long long)(cfg->ny + 2) * c->lay.pitch;
+    {
+        unsigned long long pl = (unsigned long long)(cfg->ny + 2) * (unsigned long long)c->lay.pitch;
+        if (pl * 64ull >= (1ull << 32)) { delete c; return set_err(PYH_ERR_INVALID, "block of %d x %d cells is too large for 32-bit slab offsets", cfg->nx, cfg->ny); }
+        c->lay.plane = (unsigned)pl;
+    }
     c->C.g = cfg->gamma;
     c->C.gm1 = cfg->gamma - 1.0;
     c->C.k = 1.0 / (cfg->gamma - 1.0);
@@ -299,7 +263,21 @@ int pyh_create(const pyh_config* cfg, void** out) {
         for (int k = 0; k < r && r < cfg->num_stages; ++k)
             if (c->tab.a[r * PYH_MAX_STAGES + k] != 0.0) c->need_acc[r] = true;
     }
-    if (const char* e = getenv("PYH_STAGE_KERNEL")) c->stage_kernel = (strcmp(e, "tile") == 0) ? 0 : 1;
+    {   // slab layout: plane indices -> element offsets
+        unsigned n = 0;
+        const unsigned PLn = c->lay.plane;
+        PlaneOffsets& po = c->po;
+        memset(&po, 0, sizeof(po));
+        const int nH = cfg->num_stages >= 3 ? 3 : 2;
+        for (int h = 0; h < 3; ++h) { po.H[h] = (h < nH) ? n * PLn : 0; if (h < nH) n += 4; }
+        for (int r = 0; r < cfg->num_stages; ++r) if (c->need_acc[r]) { po.P[r] = n * PLn; n += 4; }
+        po.A = n++ * PLn;
+        po.dxy = n * PLn; n += 8;
+        po.Lv = n++ * PLn; po.cv = n++ * PLn; po.sv = n++ * PLn;
+        po.Lh = n++ * PLn; po.ch = n++ * PLn; po.sh = n++ * PLn;
+        po.cdx = n++ * PLn; po.cdy = n++ * PLn;
+        po.nplanes = n;
+    }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
     Control h;
@@ -331,23 +309,12 @@ int pyh_add_block(void* ctx, const pyh_block_desc* b) {
     memset(&hb.dev, 0, sizeof(hb.dev));
     BlkDev& D = hb.dev;
     int rc;
-    for (int h = 0; h < 3; ++h) {
-        if (h == 2 && c->cfg.num_stages < 3) { D.H[h] = nullptr; continue; }
-        if ((rc = dalloc(hb, &D.H[h], 4 * L.plane, true))) return rc;
-    }
-    for (int r = 0; r < c->cfg.num_stages; ++r)
-        if (c->need_acc[r]) { if ((rc = dalloc(hb, &D.P[r], 4 * L.plane, true))) return rc; }
-    double *A, *dxy, *Lv, *cv, *sv, *Lh, *ch, *sh, *cdx, *cdy;
-    if ((rc = dalloc(hb, &A, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &dxy, 8 * L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &Lv, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &cv, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &sv, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &Lh, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &ch, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &sh, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &cdx, L.plane, true))) return rc;
-    if ((rc = dalloc(hb, &cdy, L.plane, true))) return rc;
+    double* slab = nullptr;
+    if ((rc = dalloc(hb, &slab, (long long)c->po.nplanes * L.plane, true))) return rc;
+    D.base = slab;
+    const PlaneOffsets& po = c->po;
+    double *A = slab + po.A, *dxy = slab + po.dxy, *Lv = slab + po.Lv, *cv = slab + po.cv, *sv = slab + po.sv;
+    double *Lh = slab + po.Lh, *ch = slab + po.ch, *sh = slab + po.sh, *cdx = slab + po.cdx, *cdy = slab + po.cdy;
     // stage host arrays through the scratch buffer
     size_t nn = (size_t)(ny + 1) * (nx + 1);
     if ((rc = ensure_scratch(c, 2 * nn * sizeof(double)))) return rc;
@@ -369,8 +336,8 @@ int pyh_add_block(void* ctx, const pyh_block_desc* b) {
     k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    D.A = A; D.dxy = dxy; D.Lv = Lv; D.cv = cv; D.sv = sv; D.Lh = Lh; D.ch = ch; D.sh = sh; D.cdx = cdx; D.cdy = cdy;
-    if ((rc = dalloc(hb, &D.dbg, 4 * L.plane, true))) return rc;
+    D.dbg = nullptr;
+    D.dbgG = nullptr;
     for (int s = 0; s < 4; ++s) {
         D.bc[s] = b->bc[s];
         D.nbr[s] = -1;
@@ -454,6 +421,7 @@ int pyh_destroy(void* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& hb : c->blocks) {
         for (void* p : hb.allocs) cudaFree(p);
+        if (hb.dev.dbg) cudaFree(hb.dev.dbg);
         if (hb.dev.dbgG) cudaFree(hb.dev.dbgG);
     }
     if (c->d_blks) cudaFree(c->d_blks);
@@ -482,7 +450,7 @@ int pyh_upload_state(void* ctx, int gid, const double* aos) {
     int rc = ensure_scratch(c, 4 * n * sizeof(double));
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_scratch, aos, 4 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_aos_to_soa<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, c->d_scratch, hb.dev.H[c->i0]);
+    k_aos_to_soa<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, c->d_scratch, hb.dev.base + c->po.H[c->i0]);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     c->launches++;
@@ -496,7 +464,7 @@ int pyh_download_state(void* ctx, int gid, double* aos) {
     size_t n = (size_t)c->lay.nx * c->lay.ny;
     int rc = ensure_scratch(c, 4 * n * sizeof(double));
     if (rc) return rc;
-    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.H[c->i0], c->d_scratch, 4);
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], c->d_scratch, 4);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(aos, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -511,7 +479,7 @@ int pyh_download_ghost(void* ctx, int gid, int side, double* out) {
     int len = (side == PYH_EAST || side == PYH_WEST) ? c->lay.ny : c->lay.nx;
     int rc = ensure_scratch(c, 4 * (size_t)len * sizeof(double));
     if (rc) return rc;
-    k_ghost_strip_fetch<<<cdiv(len, 128), 128, 0, c->stream>>>(c->lay, hb.dev.H[c->i0], side, c->d_scratch);
+    k_ghost_strip_fetch<<<cdiv(len, 128), 128, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], side, c->d_scratch);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, c->d_scratch, 4 * (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -555,7 +523,7 @@ int pyh_pack_halo(void* ctx, double* dev_send) {
     CU(cudaSetDevice(c->cfg.device));
     int m = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
-    k_pack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->cur, c->d_slots, dev_send);
+    k_pack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[c->cur], c->d_slots, dev_send);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -568,7 +536,7 @@ int pyh_unpack_halo(void* ctx, const double* dev_recv) {
     CU(cudaSetDevice(c->cfg.device));
     int m = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
-    k_unpack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->cur, c->d_slots, dev_recv);
+    k_unpack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[c->cur], c->d_slots, dev_recv);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -724,15 +692,42 @@ int pyh_realizable(void* ctx, int32_t* ok_out) {
     return 0;
 }
 
+static int ensure_debug_buffers(Ctx* c, bool grad) {
+    bool changed = false;
+    for (auto& b : c->blocks) {
+        if (!b.dev.dbg) {
+            void* q;
+            CU(cudaMalloc(&q, 4 * (size_t)c->lay.plane * sizeof(double)));
+            CU(cudaMemset(q, 0, 4 * (size_t)c->lay.plane * sizeof(double)));
+            b.dev.dbg = (double*)q;
+            changed = true;
+        }
+        if (grad && !b.dev.dbgG) {
+            void* q;
+            CU(cudaMalloc(&q, 12 * (size_t)c->lay.plane * sizeof(double)));
+            CU(cudaMemset(q, 0, 12 * (size_t)c->lay.plane * sizeof(double)));
+            b.dev.dbgG = (double*)q;
+            changed = true;
+        }
+    }
+    if (changed) {
+        std::vector<BlkDev> tmp;
+        for (auto& b : c->blocks) tmp.push_back(b.dev);
+        CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 static int residual_common(Ctx* c, int want_grad) {
-    // one stage launch whose only target is the debug buffer (R itself)
+    // one stage launch that only stores R itself (and optionally gx, gy, phi) into the debug buffers
+    int rc = ensure_debug_buffers(c, want_grad != 0);
+    if (rc) return rc;
     StagePlan p;
     memset(&p, 0, sizeof(p));
-    p.cur = c->i0; p.next = c->i0; p.u0 = c->i0;
-    p.ntargets = 1;
-    p.t[0].dst = 2;
-    int rc = set_active(c, 1);
-    if (rc) return rc;
+    p.cur = c->po.H[c->i0];
+    p.ntargets = 0;
+    p.write_residual = 1;
+    if ((rc = set_active(c, 1))) return rc;
     return launch_stage(c, p, want_grad);
 }
 
@@ -758,21 +753,6 @@ int pyh_debug_fetch(void* ctx, int gid, int what, double* aos_out) {
     if (!c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
     if (what < 0 || what > 2 || !aos_out) return set_err(PYH_ERR_INVALID, "bad selector / null pointer");
     int rc;
-    bool changed = false;
-    for (auto& b : c->blocks) {
-        if (!b.dev.dbgG) {
-            void* q;
-            CU(cudaMalloc(&q, 12 * (size_t)c->lay.plane * sizeof(double)));
-            CU(cudaMemset(q, 0, 12 * (size_t)c->lay.plane * sizeof(double)));
-            b.dev.dbgG = (double*)q;
-            changed = true;
-        }
-    }
-    if (changed) {
-        std::vector<BlkDev> tmp;
-        for (auto& b : c->blocks) tmp.push_back(b.dev);
-        CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
-    }
     if ((rc = residual_common(c, 1))) return rc;
     size_t n = (size_t)c->lay.nx * c->lay.ny;
     if ((rc = ensure_scratch(c, 4 * n * sizeof(double)))) return rc;

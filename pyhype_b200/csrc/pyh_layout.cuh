@@ -3,9 +3,14 @@
 // Every per-block array is a "plane": (ny + 2) rows x pitch doubles.  Cell (i, j), i in [-1, ny],
 // j in [-1, nx] lives at  (i + 1) * pitch + PADL + j ; the frame of index -1 / ny / nx is the
 // one-cell ghost layer (blocks/ghost.py keeps it in four separate GhostBlock states).  PADL = 2
-// puts interior column 0 on a 16-byte boundary.  A conserved-state buffer is 4 consecutive
-// planes (SoA: rho, rho*u, rho*v, e).  Vertical-face arrays use column J in [0, nx] of row i,
-// horizontal-face arrays use row I in [0, ny] of column j, through the same formula.
+// puts interior column 0 on a 16-byte boundary.  Vertical-face arrays use column J in [0, nx] of
+// row i, horizontal-face arrays use row I in [0, ny] of column j, through the same formula.
+//
+// All planes of one block live in ONE slab (one cudaMalloc); a plane is addressed as
+// base[plane_offset + cell_offset] with 32-bit element offsets taken from the kernel parameter
+// space (PlaneOffsets, same for every block), so a kernel needs one pointer per block and no
+// descriptor reloads inside its loops.  A conserved-state buffer is 4 consecutive planes (SoA:
+// rho, rho*u, rho*v, e).
 #pragma once
 #include <stdint.h>
 #include "../../include/pyh_b200.h"
@@ -16,22 +21,34 @@ constexpr int PADL = 2;
 
 struct Layout {
     int nx, ny, pitch;
-    long long plane;  // doubles per plane
-    __host__ __device__ inline long long at(int i, int j) const { return (long long)(i + 1) * pitch + PADL + j; }
+    unsigned plane;  // doubles per plane
+    __host__ __device__ inline unsigned at(int i, int j) const { return (unsigned)((i + 1) * pitch + PADL + j); }
+};
+
+// element offsets (plane index * plane size) inside a block slab
+struct PlaneOffsets {
+    unsigned H[3];                 // haloed conserved-state buffers (4 planes each)
+    unsigned P[PYH_MAX_STAGES];    // RK partial-sum accumulators (4 planes each), 0 if unused
+    unsigned A;                    // cell area
+    unsigned dxy;                  // 8 planes: (x_f - x_c, y_f - y_c) for f = E, W, N, S
+    unsigned Lv, cv, sv;           // vertical faces (E/W): length, cos(theta), sin(theta)
+    unsigned Lh, ch, sh;           // horizontal faces (N/S)
+    unsigned cdx, cdy;             // CFL lengths
+    unsigned nplanes;
 };
 
 struct RkTarget {
-    int src;   // 0: U0 buffer, 1: accumulator P[row]
-    int dst;   // 0: next haloed state buffer, 1: accumulator P[row], 2: debug buffer (writes R itself)
-    int row;   // tableau row s' this target belongs to
-    int add;   // 1: out = src + coef * R ; 0: out = src (a[s'][s] == 0 but the row ends here)
-    int coef;  // index into the device coefficient table (row * PYH_MAX_STAGES + stage)
+    unsigned src;  // slab offset of the 4-plane source (U0 buffer or accumulator)
+    unsigned dst;  // slab offset of the 4-plane destination (next state buffer or accumulator)
+    int add;       // 1: out = src + coef * R ; 0: out = src (a[r][s] == 0 but the row ends here)
+    int coef;      // index into the device coefficient table (row * PYH_MAX_STAGES + stage)
 };
 
 struct StagePlan {
     int ntargets;
-    int cur, next, u0;  // indices into BlkDev::H
-    RkTarget t[PYH_MAX_STAGES + 1];
+    int write_residual;   // test hook: also store R itself into BlkDev::dbg
+    unsigned cur;         // slab offset of the state buffer this stage reads
+    RkTarget t[PYH_MAX_STAGES];
 };
 
 // device-resident control block of the time loop
@@ -46,15 +63,9 @@ struct Control {
 };
 
 struct BlkDev {
-    double* H[3];                 // haloed conserved-state buffers (4 planes each)
-    double* P[PYH_MAX_STAGES];    // RK partial-sum accumulators (4 planes each) or nullptr
-    double* dbg;                  // 4 planes scratch for test hooks
+    double* base;                 // the block's slab
+    double* dbg;                  // 4 planes: residual test hook (allocated on demand)
     double* dbgG;                 // 12 planes: gx[4], gy[4], phi[4] (allocated on demand)
-    const double* A;              // cell area
-    const double* dxy;            // 8 planes: (x_f - x_c, y_f - y_c) for f = E, W, N, S
-    const double* Lv; const double* cv; const double* sv;   // vertical faces (E/W)
-    const double* Lh; const double* ch; const double* sh;   // horizontal faces (N/S)
-    const double* cdx; const double* cdy;                   // CFL lengths
     const double* dir_recon[4];   // Dirichlet strips in reconstruction variables (edge_len x 4, AoS)
     const double* dir_cons[4];    // Dirichlet strips in conservative variables
     int bc[4];

@@ -1,68 +1,101 @@
-// pyh_stage_march.cuh -- fused RK-stage kernel, row-marching version (sm_100a, fp64).
+// pyh_stage_march.cuh -- fused RK-stage kernel of the MUSCL residual (sm_100a, fp64), row-marching.
 //
-// One thread owns one mesh column of a strip and marches south -> north, keeping the 3-row state
-// window, the previous row's north-face state and the previous row's integrated fluxes in
-// registers.  Per row the CTA exchanges three small things through shared memory: the row's
-// reconstruction variables (for the x-neighbours of the gradient / min-max stencil), the east-face
-// states (left Riemann state of the next column) and the west-face integrated fluxes (= east-face
-// flux of the previous column).  Two block barriers per row, no div/mod index arithmetic, no tile
-// halo recomputation in y (one extra gradient row per strip end), two ring lanes in x.
+// Reference: fvm/base.py:108-500 (dUdt, flux sweeps), fvm/SecondOrderMUSCL.py (reconstruction),
+// limiters/base.py + limiters/limiters.py, gradients/greengauss.py, blocks/quad_block.py:120-218,
+// time_marching/explicit_runge_kutta.py:63-89 -- one launch per RK stage for ALL local blocks.
 //
-// Thread t of a CTA <-> column j = blockIdx.x * (NT - 2) - 1 + t.  Lanes 1..NT-2 produce output
-// cells; lane 0 only supplies the east-face state of column j0-1, lane NT-1 supplies the flux of
-// the face between the last output column and its east neighbour.  Ghost columns (-1, nx) are
-// carried by a lane like any other column: they publish the ghost value and, for j == nx, compute
-// the block's east-edge face flux.
+// Work decomposition.  grid = (column strips, row strips, blocks).  A CTA of NT threads owns NT-4
+// output columns and `tys` rows of one block; thread t <-> column j = strip_origin - 2 + t and
+// marches south -> north.  Lane roles: 0 and NT-1 only publish their column's reconstruction
+// variables; 1 and NT-2 additionally evaluate gradient + limiter (their face states are the outer
+// Riemann states of the first / last output column), NT-2 also the flux of its west face; lanes
+// 2..NT-3 produce output cells.  Ghost columns (-1, nx) ride on whatever lane they fall on: they
+// publish the ghost value, and the lane at j == nx evaluates the block's east-edge face.
 //
-// Arithmetic is identical to k_stage_tile (same device functions, same operation order).
+// Everything that is carried from row to row lives in shared-memory rings (3 rows of state, 2 rows
+// of east-face states / west-face fluxes / north-face states, 1 row of south-face fluxes), so the
+// register file only holds one phase's working set and there is ONE block barrier per row:
+//     top : publish row r+1 (loaded one iteration ago), issue the loads of row r+2
+//     B(r): gradient, limiter, limited face states of cell (r, j)      -> sFE, sQN (+ QW, QS in registers)
+//     ---- __syncthreads ----
+//     C(r): flux of the west face (needs the east-face state of j-1), flux of the south face
+//           (needs the north-face state of row r-1)                    -> sIW, IS
+//     D(r-1): residual of cell (r-1, j) (IN = IS(r), IE = sIW[j+1] of row r-1) + RK partial sums
+//
+// Arithmetic: pyh_math.cuh.  Each phase first runs with the branch-free division/sqrt sequences
+// (Ar<true>), accumulating a validity predicate, and is re-evaluated with the plain IEEE operators
+// (Ar<false>) in the (never observed) case that an operand fell outside the fast range.
 #pragma once
+#include <type_traits>
 #include "pyh_layout.cuh"
 #include "pyh_math.cuh"
 
 namespace pyh {
 
 constexpr int MARCH_MAX_THREADS = 192;
+constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS
+
+typedef std::integral_constant<bool, true> FastTag;
+typedef std::integral_constant<bool, false> SafeTag;
 
 template <int FLUX, int LIM, int PRIM>
-__global__ void __launch_bounds__(MARCH_MAX_THREADS, 2)
-k_stage_march(const BlkDev* __restrict__ blks, Layout lay, StagePlan plan, const Control* __restrict__ ctl,
-              Consts C, int tys, int want_grad_dbg) {
+__global__ void __launch_bounds__(MARCH_MAX_THREADS, 3)
+k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+              const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg) {
     if (!ctl->active) return;
     extern __shared__ double smem[];
     const int NT = blockDim.x;
     const int t = threadIdx.x;
-    double* sQ = smem;                 // [2][4][NT]
-    double* sFE = sQ + 8 * NT;         // [4][NT]
-    double* sIW = sFE + 4 * NT;        // [4][NT]
+    double* const sQ = smem;                  // [3][4][NT]
+    double* const sFE = sQ + 12 * NT;         // [2][4][NT]
+    double* const sIW = sFE + 8 * NT;         // [2][4][NT]
+    double* const sQN = sIW + 8 * NT;         // [2][4][NT]
+    double* const sIS = sQN + 8 * NT;         // [4][NT]
 
     const BlkDev& B = blks[blockIdx.z];
-    const int nx = lay.nx, ny = lay.ny;
-    const long long PL = lay.plane;
-    const int pitch = lay.pitch;
-    const int j = (int)blockIdx.x * (NT - 2) - 1 + t;
+    double* __restrict__ const base = B.base;
+    const int bcE = B.bc[PYH_EAST], bcW = B.bc[PYH_WEST], bcN = B.bc[PYH_NORTH], bcS = B.bc[PYH_SOUTH];
+    const int cart = B.cart;
+    const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
+    const unsigned PL = lay.plane;
+    const int j = (int)blockIdx.x * (NT - 4) - 2 + t;
     const int i0 = (int)blockIdx.y * tys;
     const int i1 = min(i0 + tys, ny);
     const bool act = (j >= -1) && (j <= nx);
     const bool real = (j >= 0) && (j < nx);
-    const bool outcol = real && (t >= 1) && (t <= NT - 2);
-    const int jc = min(max(j, -1), nx);     // clamped column for addressing
-    const double* __restrict__ U = B.H[plan.cur];
-    const int cart = B.cart;
+    const bool doB = real && (t >= 1) && (t <= NT - 2);
+    const bool doV = (t >= 2) && (t <= NT - 2) && (j >= 0) && (j <= nx);   // west-face flux
+    const bool outcol = real && (t >= 2) && (t <= NT - 3);
+    const int jc = min(max(j, -1), nx);
+    const double* __restrict__ const U = base + plan.cur;
 
-    // reconstruction variables of cell (row, col); dummy for cells that do not exist (frame corners, outside)
-    auto loadQ = [&](int row, int col, double q[4]) {
-        bool ok = (row >= -1) && (row <= ny) && (col >= -1) && (col <= nx) &&
-                  !((row == -1 || row == ny) && (col == -1 || col == nx));
-        if (ok) {
-            long long o = (long long)(row + 1) * pitch + PADL + col;
+    // ---- helpers ---------------------------------------------------------------------------------
+    auto exists = [&](int row) {   // does cell (row, j) exist (interior or ghost frame without corners)?
+        return act && (row >= -1) && (row <= ny) && !((row == -1 || row == ny) && (j == -1 || j == nx));
+    };
+    auto load_raw = [&](int row, double q[4]) {
+        if (exists(row)) {
+            unsigned o = (unsigned)((row + 1) * pitch + PADL + jc);
             q[0] = U[o]; q[1] = U[o + PL]; q[2] = U[o + 2 * PL]; q[3] = U[o + 3 * PL];
-            if (PRIM) cons2prim(q, C);
         } else {
             q[0] = 1.0; q[1] = 0.0; q[2] = 0.0; q[3] = 1.0;
         }
     };
-    auto apply_bc_edge = [&](int side, int idx, double c_, double s_, double q[4]) {
-        int bc = B.bc[side];
+    // BaseBlockGhost.from_block (quad_block.py:120-134): conservative -> reconstruction variables
+    auto to_recon = [&](double q[4]) {
+        if (PRIM) {
+            double s[4] = {q[0], q[1], q[2], q[3]};
+            bool ok = true;
+            cons2prim<true>(q, C, ok);
+            if (!ok) { q[0] = s[0]; q[1] = s[1]; q[2] = s[2]; q[3] = s[3]; cons2prim<false>(q, C, ok); }
+        }
+    };
+    auto publish = [&](int slot, const double q[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sQ[(slot * 4 + k) * NT + t] = q[k];
+    };
+    // GhostBlock.apply_boundary_condition_to_state on an edge state (fvm/base.py:352-362)
+    auto apply_bc_edge = [&](int bc, int side, int idx, double c_, double s_, double q[4]) {
         if (bc == PYH_BC_REFLECTION || bc == PYH_BC_SLIPWALL) reflect(q[1], q[2], c_, s_);
         else if (bc == PYH_BC_PRIMITIVE_DIRICHLET) {
             const double* d = B.dir_recon[side] + 4 * (long long)idx;
@@ -70,192 +103,216 @@ k_stage_march(const BlkDev* __restrict__ blks, Layout lay, StagePlan plan, const
         }
     };
 
+    // ---- prologue: rows r0-1, r0 into the ring, row r0+1 in flight --------------------------------------
     const int r0 = (i0 > 0) ? i0 - 1 : i0;   // first row whose gradient is needed
-    double Qm[4], Qc[4], Qp[4];
-    double qOut[4], qOutN[4];                // outer x-neighbour of the two ring lanes (rows r, r+1)
-    const bool edge_lane = (t == 0) || (t == NT - 1);
-    const int jout = (t == 0) ? j - 1 : j + 1;
-    if (act) { loadQ(r0 - 1, jc, Qm); loadQ(r0, jc, Qc); loadQ(r0 + 1, jc, Qp); }
-    else {
-        for (int k = 0; k < 4; ++k) { Qm[k] = Qc[k] = Qp[k] = (k == 0 || k == 3) ? 1.0 : 0.0; }
-    }
-    if (edge_lane && real) { loadQ(r0, jout, qOut); loadQ(r0 + 1, jout, qOutN); }
-    else { for (int k = 0; k < 4; ++k) { qOut[k] = qOutN[k] = (k == 0 || k == 3) ? 1.0 : 0.0; } }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sQ[((r0 & 1) * 4 + k) * NT + t] = Qc[k];
+    int sm = 0, sc = 1, sp = 2;               // ring slots of rows r-1, r, r+1
+    double Qn[4];
+    load_raw(r0 - 1, Qn); to_recon(Qn); publish(sm, Qn);
+    load_raw(r0, Qn);     to_recon(Qn); publish(sc, Qn);
+    load_raw(r0 + 1, Qn);
     __syncthreads();
 
-    double QNp[4] = {1.0, 0.0, 0.0, 1.0};    // north-face state of row r-1
-    double IWp[4] = {0, 0, 0, 0}, IEp[4] = {0, 0, 0, 0}, ISp[4] = {0, 0, 0, 0};
-
     for (int r = r0; r <= i1; ++r) {
+        const int par = r & 1;
         const bool rowreal = r < ny;
-        const bool full = (r >= i0) && (r < i1);          // rows this strip outputs
-        const bool needB = rowreal && real;               // gradient / limiter / face states of (r, j)
-        const long long o = (long long)(r + 1) * pitch + PADL + jc;
+        const bool full = (r >= i0) && (r < i1);           // rows this strip outputs
+        const unsigned o = (unsigned)((r + 1) * pitch + PADL + jc);
 
-        // prefetch row r+2 (window of the next iteration) and publish row r+1 for the x-neighbours
-        double Qn[4], qOutNN[4];
-        const bool nextB = (r + 1 <= i1) && (r + 1 < ny);
-        if (act && nextB) loadQ(r + 2, jc, Qn);
+        // top: publish row r+1, prefetch row r+2
+        to_recon(Qn);
+        publish(sp, Qn);
+        if ((r + 1 <= i1) && (r + 1 < ny)) load_raw(r + 2, Qn);
         else { Qn[0] = 1.0; Qn[1] = 0.0; Qn[2] = 0.0; Qn[3] = 1.0; }
-        if (edge_lane && real && nextB) loadQ(r + 2, jout, qOutNN);
-        else { qOutNN[0] = 1.0; qOutNN[1] = 0.0; qOutNN[2] = 0.0; qOutNN[3] = 1.0; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sQ[((((r + 1) & 1)) * 4 + k) * NT + t] = Qp[k];
 
-        // ---- B(r): Green-Gauss gradient, limiter, limited face states ---------------------------
-        double QE[4], QW[4], QN[4], QS[4];
+        // ---- B(r) ------------------------------------------------------------------------------------
+        double QW[4], QS[4];
+        {
+            const double* qm_ = sQ + sm * 4 * NT;
+            const double* qc_ = sQ + sc * 4 * NT;
+            const double* qp_ = sQ + sp * 4 * NT;
+            double QE[4], QN[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { QE[k] = QW[k] = QN[k] = QS[k] = Qc[k]; }
-        if (needB) {
-            const long long oE = o + 1, oN = o + pitch;
-            double LE = B.Lv[oE], LW = B.Lv[o], LN = B.Lh[oN], LS = B.Lh[o];
-            double xlE = LE * B.cv[oE], xlW = LW * (-B.cv[o]), xlN = LN * B.ch[oN], xlS = LS * (-B.ch[o]);
-            double ylE = LE * B.sv[oE], ylW = LW * (-B.sv[o]), ylN = LN * B.sh[oN], ylS = LS * (-B.sh[o]);
-            double ia = 1.0 / B.A[o];
-            double dx[4], dy[4];
+            for (int k = 0; k < 4; ++k) { QE[k] = QW[k] = QN[k] = QS[k] = qc_[k * NT + t]; }
+            if (doB && rowreal) {
+                const unsigned oE = o + 1, oN = o + pitch;
+                // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155)
+                double LE = base[po.Lv + oE], LW = base[po.Lv + o], LN = base[po.Lh + oN], LS = base[po.Lh + o];
+                double xlE = LE * base[po.cv + oE], xlW = LW * (-base[po.cv + o]);
+                double xlN = LN * base[po.ch + oN], xlS = LS * (-base[po.ch + o]);
+                double ylE = LE * base[po.sv + oE], ylW = LW * (-base[po.sv + o]);
+                double ylN = LN * base[po.sh + oN], ylS = LS * (-base[po.sh + o]);
+                double Acell = base[po.A + o];
+                double dx[4], dy[4];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { dx[f] = B.dxy[(2 * f) * PL + o]; dy[f] = B.dxy[(2 * f + 1) * PL + o]; }
-            const double* sq = sQ + (r & 1) * 4 * NT;
+                for (int f = 0; f < 4; ++f) { dx[f] = base[po.dxy + (2 * f) * PL + o]; dy[f] = base[po.dxy + (2 * f + 1) * PL + o]; }
+                auto phaseB = [&](auto tag) -> bool {
+                    constexpr bool FAST = decltype(tag)::value;
+                    bool ok = true;
+                    double ia = Ar<FAST>::rcp(Acell, ok);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
+                        double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
+                        // face averages (quad_block.py:181-218)
+                        double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
+                        double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
+                        double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
+                        // SlopeLimiter._get_slope (limiters/base.py:47-108)
+                        double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
+                        double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
+                        double dmx = mx - q, dmn = mn - q;
+                        double term[4];
+                        double phi = 0.0;
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            term[f] = gx * dx[f] + gy * dy[f];            // blocks/base.py:283-288
+                            double davg = (q + term[f]) - q;              // limiters/base.py:99-102
+                            double pf = limiter_face<LIM, FAST>(dmx, dmn, davg, ok);
+                            phi = (f == 0) ? pf : dmin2(phi, pf);          // limiters/base.py:179-186
+                        }
+                        if (phi < 0.0) phi = 0.0;                         // limiters/base.py:187
+                        QE[k] = q + phi * term[0];                        // SecondOrderMUSCL.py:124-126
+                        QW[k] = q + phi * term[1];
+                        QN[k] = q + phi * term[2];
+                        QS[k] = q + phi * term[3];
+                        if (want_grad_dbg && full && outcol) {
+                            B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; B.dbgG[(8 + k) * (size_t)PL + o] = phi;
+                        }
+                    }
+                    return ok;
+                };
+                if (!phaseB(FastTag{})) phaseB(SafeTag{});
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                double q = Qc[k], qS = Qm[k], qN = Qp[k];
-                double qW = (t == 0) ? qOut[k] : sq[k * NT + t - 1];
-                double qE = (t == NT - 1) ? qOut[k] : sq[k * NT + t + 1];
-                double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
-                double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
-                double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
-                double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
-                double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
-                double dmx = mx - q, dmn = mn - q;
-                double term[4];
-                double phi = 0.0;
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    term[f] = gx * dx[f] + gy * dy[f];
-                    double davg = (q + term[f]) - q;
-                    double pf = limiter_fn<LIM>(slope_of(dmx, dmn, davg));
-                    phi = (f == 0) ? pf : dmin2(phi, pf);
-                }
-                if (phi < 0.0) phi = 0.0;
-                QE[k] = q + phi * term[0];
-                QW[k] = q + phi * term[1];
-                QN[k] = q + phi * term[2];
-                QS[k] = q + phi * term[3];
-                if (want_grad_dbg && full && outcol) {
-                    B.dbgG[k * PL + o] = gx; B.dbgG[(4 + k) * PL + o] = gy; B.dbgG[(8 + k) * PL + o] = phi;
-                }
+                sFE[(par * 4 + k) * NT + t] = QE[k];
+                sQN[(par * 4 + k) * NT + t] = QN[k];
             }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sFE[k * NT + t] = QE[k];
-        __syncthreads();   // S1: sFE(r) and sQ(r+1) visible
+        __syncthreads();
 
-        // ---- C(r): vertical face J = j of row r (lanes 1.., columns 0..nx) ----------------------------
-        double IW[4] = {0, 0, 0, 0};
-        if (full && (t >= 1) && (j >= 0) && (j <= nx)) {
-            double cf = B.cv[o], sf = B.sv[o], Lf = B.Lv[o];
-            double QL[4], QR[4];
+        // ---- C(r): west face J = j of row r ----------------------------------------------------------
+        double IW[4] = {0.0, 0.0, 0.0, 0.0};
+        if (full && doV) {
+            const double cf = base[po.cv + o], sf = base[po.sv + o], Lf = base[po.Lv + o];
+            double QL0[4], QR0[4];
             if (j > 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = sFE[k * NT + t - 1];
-            } else if (B.bc[PYH_WEST] == PYH_BC_NONE) {
-                const double* sq = sQ + (r & 1) * 4 * NT;
+                for (int k = 0; k < 4; ++k) QL0[k] = sFE[(par * 4 + k) * NT + t - 1];
+            } else if (bcW == PYH_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = sq[k * NT + t - 1];      // ghost cell (r, -1)
+                for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sc * 4 + k) * NT + t - 1];      // ghost cell (r, -1), fvm/base.py:305-325
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = QW[k];
-                apply_bc_edge(PYH_WEST, r, cf, sf, QL);
+                for (int k = 0; k < 4; ++k) QL0[k] = QW[k];
+                apply_bc_edge(bcW, PYH_WEST, r, cf, sf, QL0);
             }
             if (j < nx) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = QW[k];
-            } else if (B.bc[PYH_EAST] == PYH_BC_NONE) {
+                for (int k = 0; k < 4; ++k) QR0[k] = QW[k];
+            } else if (bcE == PYH_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = Qc[k];                   // ghost cell (r, nx)
+                for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (r, nx)
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = sFE[k * NT + t - 1];     // east-face state of cell (r, nx-1)
-                apply_bc_edge(PYH_EAST, r, cf, sf, QR);
+                for (int k = 0; k < 4; ++k) QR0[k] = sFE[(par * 4 + k) * NT + t - 1];    // east-face state of cell (r, nx-1)
+                apply_bc_edge(bcE, PYH_EAST, r, cf, sf, QR0);
             }
-            if (!cart) { rot(QL[1], QL[2], cf, sf); rot(QR[1], QR[2], cf, sf); }
-            if (!PRIM) { cons2prim(QL, C); cons2prim(QR, C); }
-            double F[4];
-            riemann_flux<FLUX>(QL, QR, F, C);
-            if (!cart) unrot(F[1], F[2], cf, sf);
+            if (!cart) { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }      // fvm/base.py:366-376
+            auto faceV = [&](auto tag) -> bool {
+                constexpr bool FAST = decltype(tag)::value;
+                bool ok = true;
+                double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]}, F[4];
+                riemann_flux<FLUX, PRIM, FAST>(QL, QR, F, C, ok);
+                if (!cart) unrot(F[1], F[2], cf, sf);                                    // fvm/base.py:388-390
 #pragma unroll
-            for (int k = 0; k < 4; ++k) IW[k] = Lf * (2.0 * F[k]);
+                for (int k = 0; k < 4; ++k) IW[k] = Lf * (2.0 * F[k]);                  // integrate_flux, fvm/base.py:188-190
+                return ok;
+            };
+            if (!faceV(FastTag{})) faceV(SafeTag{});
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sIW[k * NT + t] = IW[k];
+        for (int k = 0; k < 4; ++k) sIW[(par * 4 + k) * NT + t] = IW[k];
 
-        // ---- C(r): horizontal face I = r of column j (south face of row r), output columns only -------
-        double IS[4] = {0, 0, 0, 0};
+        // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
-            double cf = B.ch[o], sf = B.sh[o], Lf = B.Lh[o];
-            double QL[4], QR[4];
+            const double cf = base[po.ch + o], sf = base[po.sh + o], Lf = base[po.Lh + o];
+            double QL0[4], QR0[4];
             if (r > 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = QNp[k];
-            } else if (B.bc[PYH_SOUTH] == PYH_BC_NONE) {
+                for (int k = 0; k < 4; ++k) QL0[k] = sQN[((par ^ 1) * 4 + k) * NT + t];
+            } else if (bcS == PYH_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = Qm[k];                   // ghost cell (-1, j)
+                for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sm * 4 + k) * NT + t];          // ghost cell (-1, j)
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL[k] = QS[k];
-                apply_bc_edge(PYH_SOUTH, j, cf, sf, QL);
+                for (int k = 0; k < 4; ++k) QL0[k] = QS[k];
+                apply_bc_edge(bcS, PYH_SOUTH, j, cf, sf, QL0);
             }
             if (r < ny) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = QS[k];
-            } else if (B.bc[PYH_NORTH] == PYH_BC_NONE) {
+                for (int k = 0; k < 4; ++k) QR0[k] = QS[k];
+            } else if (bcN == PYH_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = Qc[k];                   // ghost cell (ny, j)
+                for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (ny, j)
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR[k] = QNp[k];
-                apply_bc_edge(PYH_NORTH, j, cf, sf, QR);
+                for (int k = 0; k < 4; ++k) QR0[k] = sQN[((par ^ 1) * 4 + k) * NT + t];
+                apply_bc_edge(bcN, PYH_NORTH, j, cf, sf, QR0);
             }
-            if (cart) { rot90(QL[1], QL[2]); rot90(QR[1], QR[2]); }
-            else { rot(QL[1], QL[2], cf, sf); rot(QR[1], QR[2], cf, sf); }
-            if (!PRIM) { cons2prim(QL, C); cons2prim(QR, C); }
-            double F[4];
-            riemann_flux<FLUX>(QL, QR, F, C);
-            if (cart) unrot90(F[1], F[2]); else unrot(F[1], F[2], cf, sf);
+            if (cart) { rot90(QL0[1], QL0[2]); rot90(QR0[1], QR0[2]); }                  // fvm/base.py:435-441
+            else { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }
+            double IS[4];
+            auto faceH = [&](auto tag) -> bool {
+                constexpr bool FAST = decltype(tag)::value;
+                bool ok = true;
+                double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]}, F[4];
+                riemann_flux<FLUX, PRIM, FAST>(QL, QR, F, C, ok);
+                if (cart) unrot90(F[1], F[2]); else unrot(F[1], F[2], cf, sf);          // fvm/base.py:482-486
 #pragma unroll
-            for (int k = 0; k < 4; ++k) IS[k] = Lf * (2.0 * F[k]);
-        }
+                for (int k = 0; k < 4; ++k) IS[k] = Lf * (2.0 * F[k]);
+                return ok;
+            };
+            if (!faceH(FastTag{})) faceH(SafeTag{});
 
-        // ---- D(r-1): residual + RK partial sums of cell (r-1, j) ------------------------------------------
-        if (outcol && (r - 1 >= i0)) {
-            const long long om = o - pitch;
-            double a = B.A[om];
+            // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
+            if (r - 1 >= i0) {
+                const unsigned om = o - pitch;
+                const double a = base[po.A + om];
+                double Rk[4];
+                auto resid = [&](auto tag) -> bool {
+                    constexpr bool FAST = decltype(tag)::value;
+                    bool ok = true;
+                    typename Ar<FAST>::R ra = Ar<FAST>::recip(a, ok);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double R = 0.5 * (IWp[k] - IEp[k] + ISp[k] - IS[k]) / a;
+                    for (int k = 0; k < 4; ++k) {
+                        double IWp = sIW[((par ^ 1) * 4 + k) * NT + t], IEp = sIW[((par ^ 1) * 4 + k) * NT + t + 1];
+                        double ISp = sIS[k * NT + t];
+                        Rk[k] = Ar<FAST>::div(0.5 * (IWp - IEp + ISp - IS[k]), ra, ok);
+                    }
+                    return ok;
+                };
+                if (!resid(FastTag{})) resid(SafeTag{});
+                if (plan.write_residual) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = Rk[k];
+                }
                 for (int q = 0; q < plan.ntargets; ++q) {
-                    const RkTarget& tg = plan.t[q];
-                    if (tg.dst == 2) { B.dbg[k * PL + om] = R; continue; }
-                    double src = (tg.src == 0) ? B.H[plan.u0][k * PL + om] : B.P[tg.row][k * PL + om];
-                    double out = tg.add ? src + ctl->coef[tg.coef] * R : src;
-                    if (tg.dst == 0) B.H[plan.next][k * PL + om] = out; else B.P[tg.row][k * PL + om] = out;
+                    const RkTarget tg = plan.t[q];
+                    const double cf_ = ctl->coef[tg.coef];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double src = base[tg.src + k * PL + om];
+                        base[tg.dst + k * PL + om] = tg.add ? src + cf_ * Rk[k] : src;
+                    }
                 }
             }
-        }
-        __syncthreads();   // S2: sIW(r) visible; sFE / sQ slots may be overwritten afterwards
-
-        // carry to the next row
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            IEp[k] = (t < NT - 1) ? sIW[k * NT + t + 1] : 0.0;
-            IWp[k] = IW[k];
-            ISp[k] = IS[k];
-            QNp[k] = QN[k];
-            Qm[k] = Qc[k]; Qc[k] = Qp[k]; Qp[k] = Qn[k];
-            qOut[k] = qOutN[k]; qOutN[k] = qOutNN[k];
+            for (int k = 0; k < 4; ++k) sIS[k * NT + t] = IS[k];
         }
+
+        // rotate the ring
+        const int tmp = sm; sm = sc; sc = sp; sp = tmp;
     }
 }
 

@@ -12,7 +12,7 @@ PYH_ABI_VERSION = 1
 PYH_MAX_STAGES = 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpyh_b200.so")
+LIB_PATH = os.environ.get("PYH_LIB_PATH") or os.path.join(_HERE, "lib", "libpyh_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 

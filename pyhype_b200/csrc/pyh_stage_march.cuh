@@ -32,14 +32,20 @@
 
 namespace pyh {
 
-constexpr int MARCH_MAX_THREADS = 192;
-constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS
+#ifndef PYH_MARCH_MAXT
+#define PYH_MARCH_MAXT 128
+#endif
+#ifndef PYH_MARCH_MINB
+#define PYH_MARCH_MINB 4
+#endif
+constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
+constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4 + 8;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS, sQW, sQS
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
 template <int FLUX, int LIM, int PRIM>
-__global__ void __launch_bounds__(MARCH_MAX_THREADS, 3)
+__global__ void __launch_bounds__(MARCH_MAX_THREADS, PYH_MARCH_MINB)
 k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
               const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg) {
     if (!ctl->active) return;
@@ -51,6 +57,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     double* const sIW = sFE + 8 * NT;         // [2][4][NT]
     double* const sQN = sIW + 8 * NT;         // [2][4][NT]
     double* const sIS = sQN + 8 * NT;         // [4][NT]
+    double* const sQW = sIS + 4 * NT;         // [4][NT]  west-face state of (r, j), private
+    double* const sQS = sQW + 4 * NT;         // [4][NT]  south-face state of (r, j), private
 
     const BlkDev& B = blks[blockIdx.z];
     double* __restrict__ const base = B.base;
@@ -68,6 +76,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     const bool outcol = real && (t >= 2) && (t <= NT - 3);
     const int jc = min(max(j, -1), nx);
     const double* __restrict__ const U = base + plan.cur;
+    const double* __restrict__ const G = base;   // geometry planes: read-only for the lifetime of the context
 
     // ---- helpers ---------------------------------------------------------------------------------
     auto exists = [&](int row) {   // does cell (row, j) exist (interior or ghost frame without corners)?
@@ -125,68 +134,73 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         else { Qn[0] = 1.0; Qn[1] = 0.0; Qn[2] = 0.0; Qn[3] = 1.0; }
 
         // ---- B(r) ------------------------------------------------------------------------------------
-        double QW[4], QS[4];
         {
             const double* qm_ = sQ + sm * 4 * NT;
             const double* qc_ = sQ + sc * 4 * NT;
             const double* qp_ = sQ + sp * 4 * NT;
-            double QE[4], QN[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { QE[k] = QW[k] = QN[k] = QS[k] = qc_[k * NT + t]; }
             if (doB && rowreal) {
                 const unsigned oE = o + 1, oN = o + pitch;
                 // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155)
-                double LE = base[po.Lv + oE], LW = base[po.Lv + o], LN = base[po.Lh + oN], LS = base[po.Lh + o];
-                double xlE = LE * base[po.cv + oE], xlW = LW * (-base[po.cv + o]);
-                double xlN = LN * base[po.ch + oN], xlS = LS * (-base[po.ch + o]);
-                double ylE = LE * base[po.sv + oE], ylW = LW * (-base[po.sv + o]);
-                double ylN = LN * base[po.sh + oN], ylS = LS * (-base[po.sh + o]);
-                double Acell = base[po.A + o];
+                double LE = G[po.Lv + oE], LW = G[po.Lv + o], LN = G[po.Lh + oN], LS = G[po.Lh + o];
+                double xlE = LE * G[po.cv + oE], xlW = LW * (-G[po.cv + o]);
+                double xlN = LN * G[po.ch + oN], xlS = LS * (-G[po.ch + o]);
+                double ylE = LE * G[po.sv + oE], ylW = LW * (-G[po.sv + o]);
+                double ylN = LN * G[po.sh + oN], ylS = LS * (-G[po.sh + o]);
+                double Acell = G[po.A + o];
                 double dx[4], dy[4];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) { dx[f] = base[po.dxy + (2 * f) * PL + o]; dy[f] = base[po.dxy + (2 * f + 1) * PL + o]; }
-                auto phaseB = [&](auto tag) -> bool {
-                    constexpr bool FAST = decltype(tag)::value;
-                    bool ok = true;
-                    double ia = Ar<FAST>::rcp(Acell, ok);
+                for (int f = 0; f < 4; ++f) { dx[f] = G[po.dxy + (2 * f) * PL + o]; dy[f] = G[po.dxy + (2 * f + 1) * PL + o]; }
+                bool okA = true;
+                double ia = Ar<true>::rcp(Acell, okA);
+                if (!okA) ia = 1.0 / Acell;
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
+                    const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
+                    // face averages (quad_block.py:181-218)
+                    double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
+                    double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
+                    double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
+                    // SlopeLimiter._get_slope (limiters/base.py:47-108)
+                    double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
+                    double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
+                    double dmx = mx - q, dmn = mn - q;
+                    double term[4], davg[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
-                        double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
-                        // face averages (quad_block.py:181-218)
-                        double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
-                        double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
-                        double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
-                        // SlopeLimiter._get_slope (limiters/base.py:47-108)
-                        double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
-                        double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
-                        double dmx = mx - q, dmn = mn - q;
-                        double term[4];
-                        double phi = 0.0;
+                    for (int f = 0; f < 4; ++f) {
+                        term[f] = gx * dx[f] + gy * dy[f];                // blocks/base.py:283-288
+                        davg[f] = (q + term[f]) - q;                      // limiters/base.py:99-102
+                    }
+                    double phi;
+                    auto limit = [&](auto tag) -> bool {
+                        constexpr bool FAST = decltype(tag)::value;
+                        bool ok = true;
 #pragma unroll
                         for (int f = 0; f < 4; ++f) {
-                            term[f] = gx * dx[f] + gy * dy[f];            // blocks/base.py:283-288
-                            double davg = (q + term[f]) - q;              // limiters/base.py:99-102
-                            double pf = limiter_face<LIM, FAST>(dmx, dmn, davg, ok);
+                            double pf = limiter_face<LIM, FAST>(dmx, dmn, davg[f], ok);
                             phi = (f == 0) ? pf : dmin2(phi, pf);          // limiters/base.py:179-186
                         }
-                        if (phi < 0.0) phi = 0.0;                         // limiters/base.py:187
-                        QE[k] = q + phi * term[0];                        // SecondOrderMUSCL.py:124-126
-                        QW[k] = q + phi * term[1];
-                        QN[k] = q + phi * term[2];
-                        QS[k] = q + phi * term[3];
-                        if (want_grad_dbg && full && outcol) {
-                            B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; B.dbgG[(8 + k) * (size_t)PL + o] = phi;
-                        }
+                        return ok;
+                    };
+                    if (!limit(FastTag{})) limit(SafeTag{});
+                    if (phi < 0.0) phi = 0.0;                             // limiters/base.py:187
+                    sFE[(par * 4 + k) * NT + t] = q + phi * term[0];      // SecondOrderMUSCL.py:124-126
+                    sQW[k * NT + t] = q + phi * term[1];
+                    sQN[(par * 4 + k) * NT + t] = q + phi * term[2];
+                    sQS[k * NT + t] = q + phi * term[3];
+                    if (want_grad_dbg && full && outcol) {
+                        B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; B.dbgG[(8 + k) * (size_t)PL + o] = phi;
                     }
-                    return ok;
-                };
-                if (!phaseB(FastTag{})) phaseB(SafeTag{});
-            }
+                }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                sFE[(par * 4 + k) * NT + t] = QE[k];
-                sQN[(par * 4 + k) * NT + t] = QN[k];
+                for (int k = 0; k < 4; ++k) {
+                    const double q = qc_[k * NT + t];
+                    sFE[(par * 4 + k) * NT + t] = q;
+                    sQN[(par * 4 + k) * NT + t] = q;
+                    sQW[k * NT + t] = q;
+                    sQS[k * NT + t] = q;
+                }
             }
         }
         __syncthreads();
@@ -194,7 +208,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         // ---- C(r): west face J = j of row r ----------------------------------------------------------
         double IW[4] = {0.0, 0.0, 0.0, 0.0};
         if (full && doV) {
-            const double cf = base[po.cv + o], sf = base[po.sv + o], Lf = base[po.Lv + o];
+            const double cf = G[po.cv + o], sf = G[po.sv + o], Lf = G[po.Lv + o];
             double QL0[4], QR0[4];
             if (j > 0) {
 #pragma unroll
@@ -204,12 +218,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sc * 4 + k) * NT + t - 1];      // ghost cell (r, -1), fvm/base.py:305-325
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = QW[k];
+                for (int k = 0; k < 4; ++k) QL0[k] = sQW[k * NT + t];
                 apply_bc_edge(bcW, PYH_WEST, r, cf, sf, QL0);
             }
             if (j < nx) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = QW[k];
+                for (int k = 0; k < 4; ++k) QR0[k] = sQW[k * NT + t];
             } else if (bcE == PYH_BC_NONE) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (r, nx)
@@ -236,7 +250,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 
         // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
-            const double cf = base[po.ch + o], sf = base[po.sh + o], Lf = base[po.Lh + o];
+            const double cf = G[po.ch + o], sf = G[po.sh + o], Lf = G[po.Lh + o];
             double QL0[4], QR0[4];
             if (r > 0) {
 #pragma unroll
@@ -246,12 +260,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sm * 4 + k) * NT + t];          // ghost cell (-1, j)
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = QS[k];
+                for (int k = 0; k < 4; ++k) QL0[k] = sQS[k * NT + t];
                 apply_bc_edge(bcS, PYH_SOUTH, j, cf, sf, QL0);
             }
             if (r < ny) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = QS[k];
+                for (int k = 0; k < 4; ++k) QR0[k] = sQS[k * NT + t];
             } else if (bcN == PYH_BC_NONE) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (ny, j)
@@ -278,7 +292,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
             if (r - 1 >= i0) {
                 const unsigned om = o - pitch;
-                const double a = base[po.A + om];
+                const double a = G[po.A + om];
                 double Rk[4];
                 auto resid = [&](auto tag) -> bool {
                     constexpr bool FAST = decltype(tag)::value;

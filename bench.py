@@ -300,7 +300,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": peak_src, "kernel": "k_stage_tile", "kernel_ms_avg": kern_ms,
+            "peak_source": peak_src, "kernel": "k_stage_march", "kernel_ms_avg": kern_ms,
             "algorithmic_bytes_per_cell_stage": bytes_per_cell_stage, "cells_per_launch": cells_local,
             "fp64_pipe": {
                 "note": "bit-faithful fp64 (no FMA contraction): the FP64 pipe binds before HBM (DESIGN.md)",

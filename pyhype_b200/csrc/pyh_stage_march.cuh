@@ -32,6 +32,12 @@
 
 namespace pyh {
 
+#ifndef PYH_MARCH_PF_GEO
+#define PYH_MARCH_PF_GEO 0
+#endif
+#ifndef PYH_MARCH_PF_RK
+#define PYH_MARCH_PF_RK 0
+#endif
 #ifndef PYH_MARCH_MAXT
 #define PYH_MARCH_MAXT 128
 #endif
@@ -40,6 +46,8 @@ namespace pyh {
 #endif
 constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
 constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4 + 8;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS, sQW, sQS
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
@@ -127,6 +135,22 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         const bool full = (r >= i0) && (r < i1);           // rows this strip outputs
         const unsigned o = (unsigned)((r + 1) * pitch + PADL + jc);
 
+        // L2 prefetch (no register cost) one row ahead of use: geometry of row r+1, RK sources of row r
+        if (PYH_MARCH_PF_GEO && doB && (r + 1 < ny)) {
+            const unsigned op = o + pitch;
+            prefetch_l2(G + po.Lv + op); prefetch_l2(G + po.cv + op); prefetch_l2(G + po.sv + op);
+            prefetch_l2(G + po.Lh + op + pitch); prefetch_l2(G + po.ch + op + pitch); prefetch_l2(G + po.sh + op + pitch);
+            prefetch_l2(G + po.A + op);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) prefetch_l2(G + po.dxy + f * PL + op);
+        }
+        if (PYH_MARCH_PF_RK && outcol && full) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                prefetch_l2(base + plan.t[0].src + k * PL + o);
+                if (plan.ntargets > 1 && plan.t[1].src != plan.t[0].src) prefetch_l2(base + plan.t[1].src + k * PL + o);
+            }
+        }
         // top: publish row r+1, prefetch row r+2
         to_recon(Qn);
         publish(sp, Qn);
@@ -311,13 +335,32 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 #pragma unroll
                     for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = Rk[k];
                 }
-                for (int q = 0; q < plan.ntargets; ++q) {
-                    const RkTarget tg = plan.t[q];
-                    const double cf_ = ctl->coef[tg.coef];
+                {
+                    // all source loads first, then the updates (targets 0 and 1 by static index: no local copies)
+                    const int nt_ = plan.ntargets;
+                    double s0[4], s1[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        double src = base[tg.src + k * PL + om];
-                        base[tg.dst + k * PL + om] = tg.add ? src + cf_ * Rk[k] : src;
+                        s0[k] = (nt_ > 0) ? base[plan.t[0].src + k * PL + om] : 0.0;
+                        s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + om] : 0.0;
+                    }
+                    if (nt_ > 0) {
+                        const double c0 = ctl->coef[plan.t[0].coef];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) base[plan.t[0].dst + k * PL + om] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k];
+                    }
+                    if (nt_ > 1) {
+                        const double c1 = ctl->coef[plan.t[1].coef];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) base[plan.t[1].dst + k * PL + om] = plan.t[1].add ? s1[k] + c1 * Rk[k] : s1[k];
+                    }
+                    for (int q = 2; q < nt_; ++q) {   // tableaux with more than two live rows (e.g. DormandPrince5)
+                        const double cq = ctl->coef[plan.t[q].coef];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double src = base[plan.t[q].src + k * PL + om];
+                            base[plan.t[q].dst + k * PL + om] = plan.t[q].add ? src + cq * Rk[k] : src;
+                        }
                     }
                 }
             }

@@ -1,0 +1,45 @@
+"""Launched by tests/test_gpu_multirank.py under torch.distributed.run (one rank per GPU): the
+block-sharded run through the Python facade must be bit-identical to the single-process oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+from test_gpu_facade import ExplosionInitialCondition, em_config, em_mesh  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from pyhype_b200.solvers import Euler2D
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    nx, ny = 26, 22
+    config = em_config(nx=nx, ny=ny, t_final=0.004, initial_condition=ExplosionInitialCondition())
+    sim = Euler2D(config=config, mesh_config=em_mesh())
+    sim.solve()
+    prob = cases.build_oracle(em_mesh().dict, nx, ny, cases.explosion_ic)
+    t, dts = prob.run(0.0, 0.004 * 343.0)
+    assert sim.num_time_step == len(dts) and sim.t == t, (sim.num_time_step, len(dts))
+    mine = [b.global_block_num for b in sim.blocks]
+    assert len(mine) == 8 // world or world > 8
+    for block in sim.blocks:
+        ref = prob.blocks[block.global_block_num]
+        assert np.array_equal(block.state.data, ref.U), f"rank {rank} block {block.global_block_num}"
+        for s in "EWNS":
+            assert np.array_equal(getattr(block.ghost, s).state.data, ref.ghost[s]), (rank, block.global_block_num, s)
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIRANK OK world={world} steps={len(dts)}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

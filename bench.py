@@ -235,7 +235,7 @@ def run_ours(args):
         # end-to-end through the host-buffer API: every step uploads the state from pinned host
         # memory, advances one time step and reads the result back to the host
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        out_host = {gid: np.empty((n, n, 4)) for gid in mine}
+        out_host = {gid: torch.empty((n, n, 4), dtype=torch.float64, pin_memory=True).numpy() for gid in mine}
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -243,7 +243,7 @@ def run_ours(args):
             refresh_ghosts()
             one_step()
             for gid in mine:
-                out_host[gid][...] = eng.download(gid)
+                eng.download(gid, out=out_host[gid])
         barrier()
         e2e_s = time.perf_counter() - t0
 
@@ -294,7 +294,7 @@ def run_ours(args):
             "value": e2e_value, "unit": "cell-stage updates/s",
             "h2d_bytes_per_step": cells_total * 32, "d2h_bytes_per_step": cells_total * 32,
             "steps": e2e_steps,
-            "how": "per step: upload all block states from pinned host memory (pyh_upload_state), ghost refresh, one time step, download all block states (pyh_download_state); wall clock, max over ranks",
+            "how": "per step: upload all block states from pinned host memory (pyh_upload_state), ghost refresh, one time step, download all block states into pinned host memory (pyh_download_state); wall clock, max over ranks",
         },
         "gpu_launches": launches_total,
         "clocks": clocks,

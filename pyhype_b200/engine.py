@@ -114,8 +114,13 @@ class Engine:
             raise ValueError(f"state must have shape {(self.ny, self.nx, 4)}, got {a.shape}")
         check(self.lib.pyh_upload_state(self._ctx, int(gid), _dp(a)))
 
-    def download(self, gid):
-        out = np.empty((self.ny, self.nx, 4))
+    def download(self, gid, out=None):
+        """Conservative state of block ``gid`` as (ny, nx, 4); ``out`` may be a caller-owned
+        (e.g. pinned) C-contiguous float64 array to receive it without an extra copy."""
+        if out is None:
+            out = np.empty((self.ny, self.nx, 4))
+        elif out.shape != (self.ny, self.nx, 4) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (ny, nx, 4)")
         check(self.lib.pyh_download_state(self._ctx, int(gid), _dp(out)))
         return out
 

@@ -35,7 +35,11 @@ for row in src[2:]:
     if len(row) <= iex: continue
     s = re.sub(r"^@!?U?P\d+\s+", "", row[isrc].strip())
     op = s.split()[0].split(".")[0] if s else "?"
-    n = int(row[iex]); agg[op] += n; tot += n
+    try:
+        n = int(row[iex])
+    except ValueError:
+        break  # next kernel's header: only the first captured launch is summarised
+    agg[op] += n; tot += n
 print(f"dynamic opcode mix (warp instructions, total {tot}, static {len(src) - 2}):")
 fp64 = sum(agg[o] for o in ("DFMA", "DMUL", "DADD", "DSETP"))
 print(f"  FP64 (DFMA+DMUL+DADD+DSETP) {fp64 / tot * 100:5.1f}%")

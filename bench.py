@@ -332,25 +332,79 @@ def cpu_sample_problem(args, nblk_side):
     return prob
 
 
-def cpu_baseline(args, seconds=15.0, steps=None):
-    """Times the numpy port of the reference (oracle/muscl_oracle.py, one core like the reference's
-    serial numba/numpy kernels) on a bounded sample: same workload at reduced block size."""
-    side = args.cpu_block
-    prob = cpu_sample_problem(args, side)
-    nstages = len(prob.tableau)
-    cells = len(prob.blocks) * side * side
-    prob.step(prob.get_dt(0.0, 1e9))  # warm-up (page-in, allocator)
-    n = 0
+def _cpu_worker(rank, world, port, argd, seconds, steps, ret):
+    import torch
+    import torch.distributed as dist
+
+    from oracle.sharded import OracleShardEngine
+    from pyhype_b200.distributed import HaloExchanger, advance, distribute_blocks
+
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nb, side = argd["blocks_per_gpu"], argd["cpu_block"]
+    blocks = ws_mesh(1, nb)
+    owner = distribute_blocks(len(blocks), world)
+    eng = OracleShardEngine(blocks, side, side, owner, rank, lambda x, y: ws_ic(x, y, BLOCK_LEN * nb, BLOCK_LEN),
+                            flux=argd["flux"], limiter="Venkatakrishnan", recon="conservative",
+                            integrator=argd["integrator"], CFL=0.7)
+    hx = HaloExchanger(eng, owner, rank, backend_device=torch.device("cpu"))
+
+    def one_step():
+        dt = hx.global_dt()
+        advance(eng, hx, eng.num_stages, dt_dev_ptr=dt.data_ptr())
+
+    hx.exchange()
+    eng.apply_bc()
+    one_step()  # warm-up
+    dist.barrier()
+    if steps is None:  # calibrate the step count for ~`seconds` of work
+        t0 = time.perf_counter()
+        one_step()
+        dist.barrier()
+        el = torch.tensor([time.perf_counter() - t0])
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        steps = max(2, min(400, int(seconds / max(float(el[0]), 1e-3))))
+    dist.barrier()
     t0 = time.perf_counter()
-    while True:
-        prob.step(prob.get_dt(0.0, 1e9))
-        n += 1
-        el = time.perf_counter() - t0
-        if (steps is not None and n >= steps) or (steps is None and el >= seconds):
-            break
+    for _ in range(steps):
+        one_step()
+    dist.barrier()
+    el = torch.tensor([time.perf_counter() - t0])
+    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ret["seconds"] = float(el[0])
+        ret["steps"] = steps
+        ret["stages"] = eng.num_stages
+    dist.destroy_process_group()
+
+
+def cpu_baseline(args, seconds=15.0, steps=None):
+    """Times the numpy port of the reference (oracle/, kind "port") on the host cores, on a bounded
+    sample of the workload (same mesh / IC / scheme at reduced block size).  Like the reference under
+    `mpiexec -n P` it runs one single-threaded process per block group (P = min(cores, blocks)),
+    exchanging ghost strips every RK stage and reducing dt every step -- over gloo instead of MPI
+    (oracle/sharded.py)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    side, nb = args.cpu_block, args.blocks_per_gpu
+    nproc = max(1, min(os.cpu_count() or 1, nb, args.cpu_procs if args.cpu_procs > 0 else 1 << 30))
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    argd = dict(blocks_per_gpu=nb, cpu_block=side, flux=args.flux, integrator=args.integrator)
+    mp.spawn(_cpu_worker, args=(nproc, port, argd, seconds, steps, ret), nprocs=nproc, join=True)
+    cells = nb * side * side
+    n, el, nstages = ret["steps"], ret["seconds"], ret["stages"]
     return {
-        "value": cells * nstages * n / el, "unit": "cell-stage updates/s", "cores": 1, "kind": "port",
-        "sample": f"{len(prob.blocks)} blocks of {side}x{side} (same mesh/IC/scheme as the workload at reduced block size), {n} {args.integrator} steps, {el:.1f} s",
+        "value": cells * nstages * n / el, "unit": "cell-stage updates/s", "cores": nproc, "kind": "port",
+        "sample": f"{nb} blocks of {side}x{side} (same mesh/IC/scheme as the workload at reduced block size), {n} {args.integrator} steps, {el:.1f} s, {nproc} single-threaded processes (block-sharded like mpiexec -n {nproc}, ghost exchange + dt reduction over gloo)",
         "host_cores_available": os.cpu_count(),
     }
 
@@ -359,11 +413,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = []
-    for _ in range(args.warmup):
-        cpu_baseline(args, steps=1)
-    t0 = time.perf_counter()
-    cb = cpu_baseline(args, steps=args.steps)
+    cb = cpu_baseline(args, steps=args.steps)  # each worker does its own untimed warm-up step
     nstages = 4 if args.integrator == "RK4" else len(__import__("oracle.muscl_oracle", fromlist=["TABLEAUX"]).TABLEAUX[args.integrator])
     side = args.cpu_block
     cells = args.blocks_per_gpu * side * side
@@ -396,6 +446,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-block", type=int, default=192, help="block side of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = min(cores, blocks))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -32,12 +32,6 @@
 
 namespace pyh {
 
-#ifndef PYH_MARCH_PF_GEO
-#define PYH_MARCH_PF_GEO 0
-#endif
-#ifndef PYH_MARCH_PF_RK
-#define PYH_MARCH_PF_RK 0
-#endif
 #ifndef PYH_MARCH_MAXT
 #define PYH_MARCH_MAXT 128
 #endif
@@ -46,8 +40,6 @@ namespace pyh {
 #endif
 constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
 constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4 + 8;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS, sQW, sQS
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
@@ -135,23 +127,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         const bool full = (r >= i0) && (r < i1);           // rows this strip outputs
         const unsigned o = (unsigned)((r + 1) * pitch + PADL + jc);
 
-        // L2 prefetch (no register cost) one row ahead of use: geometry of row r+1, RK sources of row r
-        if (PYH_MARCH_PF_GEO && doB && (r + 1 < ny)) {
-            const unsigned op = o + pitch;
-            prefetch_l2(G + po.Lv + op); prefetch_l2(G + po.cv + op); prefetch_l2(G + po.sv + op);
-            prefetch_l2(G + po.Lh + op + pitch); prefetch_l2(G + po.ch + op + pitch); prefetch_l2(G + po.sh + op + pitch);
-            prefetch_l2(G + po.A + op);
-#pragma unroll
-            for (int f = 0; f < 8; ++f) prefetch_l2(G + po.dxy + f * PL + op);
-        }
-        if (PYH_MARCH_PF_RK && outcol && full) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                prefetch_l2(base + plan.t[0].src + k * PL + o);
-                if (plan.ntargets > 1 && plan.t[1].src != plan.t[0].src) prefetch_l2(base + plan.t[1].src + k * PL + o);
-            }
-        }
-        // top: publish row r+1, prefetch row r+2
+        // top: publish row r+1, issue the loads of row r+2 (L2 prefetch hints were measured and hurt: profiles/r01h_summary.md)
         to_recon(Qn);
         publish(sp, Qn);
         if ((r + 1 <= i1) && (r + 1 < ny)) load_raw(r + 2, Qn);

@@ -211,8 +211,7 @@ int set_active(Ctx* c, int active) {
 }
 
 int launch_dt(Ctx* c, int buf, int respect_active = 0) {
-    long long total = (long long)c->lay.nx * c->lay.ny * (long long)c->blocks.size();
-    int grid = (int)std::min<long long>(cdiv(total, 256), 148 * 8);
+    dim3 grid(cdiv(c->lay.nx, 256), cdiv(c->lay.ny, DT_ROWS), (unsigned)c->blocks.size());
     k_dt<<<grid, 256, 0, c->stream>>>(c->d_blks, c->lay, c->po, c->po.H[buf], (int)c->blocks.size(), c->d_ctl, c->C, respect_active);
     CU(cudaGetLastError());
     c->launches++;

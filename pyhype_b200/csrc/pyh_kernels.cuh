@@ -6,6 +6,7 @@
 //                (quad_block.py:423-436, solvers/base.py:114-136, Euler2D.py:195-210)
 #pragma once
 #include "pyh_layout.cuh"
+#include <type_traits>
 #include "pyh_math.cuh"
 
 namespace pyh {
@@ -107,29 +108,38 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
 }
 constexpr unsigned long long DKEY_INF = 0xfff0000000000000ull;  // dkey(+inf)
 
+constexpr int DT_ROWS = 16;
+
 __global__ void __launch_bounds__(256)
 k_dt(const BlkDev* __restrict__ blks, Layout lay, PlaneOffsets po, unsigned buf, int nblk, Control* __restrict__ ctl, Consts C, int respect_active) {
     if (respect_active && !ctl->active) return;
     const int nx = lay.nx, ny = lay.ny;
-    const long long ncell = (long long)nx * ny;
-    const long long total = ncell * nblk;
     const unsigned PL = lay.plane;
     double m = __longlong_as_double(0x7ff0000000000000ll);
     int bad = 0;
-    for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < total; n += (long long)gridDim.x * blockDim.x) {
-        int b = (int)(n / ncell);
-        long long r = n - (long long)b * ncell;
-        int i = (int)(r / nx), j = (int)(r - (long long)i * nx);
-        const BlkDev& B = blks[b];
+    // grid = (column chunks of blockDim.x, row groups of DT_ROWS, blocks): no per-cell index division
+    const BlkDev& B = blks[blockIdx.z];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ibeg = blockIdx.y * DT_ROWS, iend = min(ibeg + DT_ROWS, ny);
+    for (int i = ibeg; i < iend && j < nx; ++i) {
         unsigned o = lay.at(i, j);
         const double* U = B.base + buf;
         double rho = U[o], ru = U[o + PL], rv = U[o + 2 * PL], e = U[o + 3 * PL];
         if (!(rho > 0.0) || !(e > 0.0)) bad = 1;
-        double u = ru / rho, v = rv / rho;
-        double p = C.gm1 * (e - rho * (0.5 * (u * u + v * v)));
-        double a = sqrt(C.g * p / rho);
-        double tx = B.base[po.cdx + o] / (fabs(u) + a);
-        double ty = B.base[po.cdy + o] / (fabs(v) + a);
+        const double cdx = B.base[po.cdx + o], cdy = B.base[po.cdy + o];
+        double tx, ty;
+        auto cfl = [&](auto tag) -> bool {
+            constexpr bool FAST = decltype(tag)::value;
+            bool ok = true;
+            typename Ar<FAST>::R rr = Ar<FAST>::recip(rho, ok);
+            double u = Ar<FAST>::div(ru, rr, ok), v = Ar<FAST>::div(rv, rr, ok);
+            double p = C.gm1 * (e - rho * (0.5 * (u * u + v * v)));
+            double a = Ar<FAST>::sqrt(Ar<FAST>::div(C.g * p, rr, ok), ok);
+            tx = Ar<FAST>::div(cdx, fabs(u) + a, ok);
+            ty = Ar<FAST>::div(cdy, fabs(v) + a, ok);
+            return ok;
+        };
+        if (!cfl(std::integral_constant<bool, true>{})) cfl(std::integral_constant<bool, false>{});
         double tm = dmin2(tx, ty);
         if (tm != tm) bad = 1;
         m = dmin2(m, tm);

@@ -153,6 +153,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 bool okA = true;
                 double ia = Ar<true>::rcp(Acell, okA);
                 if (!okA) ia = 1.0 / Acell;
+                // pass 1: gradient and the high-order terms of the four faces; the terms wait in this
+                // thread's own face-state slots so that no geometry is live while the limiter divides
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
@@ -161,36 +163,35 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
                     double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
                     double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
-                    // SlopeLimiter._get_slope (limiters/base.py:47-108)
+                    sFE[(par * 4 + k) * NT + t] = gx * dx[0] + gy * dy[0];       // blocks/base.py:283-288
+                    sQW[k * NT + t] = gx * dx[1] + gy * dy[1];
+                    sQN[(par * 4 + k) * NT + t] = gx * dx[2] + gy * dy[2];
+                    sQS[k * NT + t] = gx * dx[3] + gy * dy[3];
+                    if (want_grad_dbg && full && outcol) { B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; }
+                }
+                // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
+                    const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
+                    double term[4], davg[4];
+                    term[0] = sFE[(par * 4 + k) * NT + t];
+                    term[1] = sQW[k * NT + t];
+                    term[2] = sQN[(par * 4 + k) * NT + t];
+                    term[3] = sQS[k * NT + t];
                     double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
                     double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
                     double dmx = mx - q, dmn = mn - q;
-                    double term[4], davg[4];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        term[f] = gx * dx[f] + gy * dy[f];                // blocks/base.py:283-288
-                        davg[f] = (q + term[f]) - q;                      // limiters/base.py:99-102
-                    }
+                    for (int f = 0; f < 4; ++f) davg[f] = (q + term[f]) - q;      // limiters/base.py:99-102
                     double phi;
-                    auto limit = [&](auto tag) -> bool {
-                        constexpr bool FAST = decltype(tag)::value;
-                        bool ok = true;
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) {
-                            double pf = limiter_face<LIM, FAST>(dmx, dmn, davg[f], ok);
-                            phi = (f == 0) ? pf : dmin2(phi, pf);          // limiters/base.py:179-186
-                        }
-                        return ok;
-                    };
-                    if (!limit(FastTag{})) limit(SafeTag{});
-                    if (phi < 0.0) phi = 0.0;                             // limiters/base.py:187
-                    sFE[(par * 4 + k) * NT + t] = q + phi * term[0];      // SecondOrderMUSCL.py:124-126
+                    if (!limiter4_fast<LIM>(dmx, dmn, davg, phi)) limiter4_safe<LIM>(dmx, dmn, davg, phi);
+                    if (phi < 0.0) phi = 0.0;                                     // limiters/base.py:187
+                    sFE[(par * 4 + k) * NT + t] = q + phi * term[0];              // SecondOrderMUSCL.py:124-126
                     sQW[k * NT + t] = q + phi * term[1];
                     sQN[(par * 4 + k) * NT + t] = q + phi * term[2];
                     sQS[k * NT + t] = q + phi * term[3];
-                    if (want_grad_dbg && full && outcol) {
-                        B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; B.dbgG[(8 + k) * (size_t)PL + o] = phi;
-                    }
+                    if (want_grad_dbg && full && outcol) B.dbgG[(8 + k) * (size_t)PL + o] = phi;
                 }
             } else {
 #pragma unroll

@@ -105,11 +105,16 @@ MarchFn mpick_l(int l, int p) {
     }
 }
 MarchFn pick_march(int f, int l, int p) {
+#ifdef PYH_ONLY_ROE_VENKAT_CONS   // kernel-tuning builds (tools/build_variant.sh): one instantiation, 10x faster to compile
+    (void)f; (void)l; (void)p;
+    return k_stage_march<0, 0, 0>;
+#else
     switch (f) {
         case 0: return mpick_l<0>(l, p);
         case 1: return mpick_l<1>(l, p);
         default: return mpick_l<2>(l, p);
     }
+#endif
 }
 
 // lanes per CTA: two ring lanes per strip, so pick the width that wastes the fewest lanes for this nx

@@ -152,6 +152,7 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
     for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
     if (!done) {
         CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM_DOUBLES_PER_THREAD * MARCH_MAX_THREADS * (int)sizeof(double)));
+        if (const char* e = getenv("PYH_CARVEOUT")) CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         if (nconf < 64) configured[nconf++] = fn;
     }
     dim3 grid(cdiv(c->lay.nx, nt - 4), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());

@@ -22,6 +22,7 @@
 #ifndef PYH_B200_H
 #define PYH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -104,6 +105,27 @@ int pyh_destroy(void* ctx);
 /* block.state.data setter / getter (pyhype/states/base.py:84-90) */
 int pyh_upload_state(void* ctx, int gid, const double* aos);
 int pyh_download_state(void* ctx, int gid, double* aos);
+/* Asynchronous variants for streaming use (replaces nothing in the reference, which keeps state on the
+ * host; serves Solver.write_solution, pyhype/solvers/base.py:158-172, without stalling the time loop,
+ * and back-to-back independent runs).  Host buffers should be page-locked; they are read / written
+ * until the matching pyh_transfers_sync returns.
+ *   pyh_upload_state_async : enqueue the H2D copy of one block's (ny, nx, 4) state into a device staging
+ *                            area on the context's copy-in stream; returns immediately.
+ *   pyh_commit_uploads     : make the compute stream wait for the staged copies and convert them into the
+ *                            current solution buffers (AoS -> SoA planes); returns immediately.
+ *   pyh_download_state_async: convert the current solution of one block into a staging area on the compute
+ *                            stream, then copy it to `aos` on the copy-out stream; returns immediately.
+ *   pyh_transfers_sync     : block until every copy enqueued so far has completed. */
+int pyh_upload_state_async(void* ctx, int gid, const double* aos);
+int pyh_commit_uploads(void* ctx);
+int pyh_download_state_async(void* ctx, int gid, double* aos);
+int pyh_transfers_sync(void* ctx);
+/* Block until every pyh_download_state_async copy enqueued so far has landed, WITHOUT waiting for
+ * compute enqueued after it (may be called from a second host thread, e.g. an output writer). */
+int pyh_downloads_sync(void* ctx);
+/* Page-locked host memory for the asynchronous copies (cudaHostAlloc / cudaFreeHost). */
+int pyh_host_alloc(size_t bytes, void** out);
+int pyh_host_free(void* p);
 /* ghost strips as the reference keeps them: out is (edge_len, 4) conservative */
 int pyh_download_ghost(void* ctx, int gid, int side, double* out);
 

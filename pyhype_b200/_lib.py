@@ -64,6 +64,13 @@ SIGNATURES = {
     "pyh_destroy": (C.c_int, [_vp]),
     "pyh_upload_state": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_download_state": (C.c_int, [_vp, C.c_int, c_double_p]),
+    "pyh_upload_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
+    "pyh_commit_uploads": (C.c_int, [_vp]),
+    "pyh_download_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
+    "pyh_transfers_sync": (C.c_int, [_vp]),
+    "pyh_downloads_sync": (C.c_int, [_vp]),
+    "pyh_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "pyh_host_free": (C.c_int, [_vp]),
     "pyh_download_ghost": (C.c_int, [_vp, C.c_int, C.c_int, c_double_p]),
     "pyh_apply_bc": (C.c_int, [_vp]),
     "pyh_halo_count": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -64,7 +64,31 @@ struct Ctx {
     long long dts_cap = 0;
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
     int march_nt = 128, march_tys = 64;
+    // asynchronous state streaming (pyh_upload_state_async & co)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in_done = nullptr, ev_in_consumed = nullptr, ev_out_ready = nullptr;
+    std::vector<cudaEvent_t> ev_out_done;   // per block: the D2H copy out of its staging area has finished
+    double* d_stage_in = nullptr;           // nblocks x (ny, nx, 4)
+    double* d_stage_out = nullptr;
+    std::vector<char> staged;
 };
+
+int ensure_streaming(Ctx* c) {
+    if (c->s_in) return 0;
+    const size_t nb = c->blocks.size();
+    const size_t per = 4 * (size_t)c->lay.nx * c->lay.ny;
+    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_in_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_in_consumed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
+    c->ev_out_done.assign(nb, nullptr);
+    for (size_t b = 0; b < nb; ++b) CU(cudaEventCreateWithFlags(&c->ev_out_done[b], cudaEventDisableTiming));
+    CU(cudaMalloc(&c->d_stage_in, nb * per * sizeof(double)));
+    CU(cudaMalloc(&c->d_stage_out, nb * per * sizeof(double)));
+    c->staged.assign(nb, 0);
+    return 0;
+}
 
 int ensure_scratch(Ctx* c, size_t bytes) {
     if (c->scratch_bytes >= bytes) return 0;
@@ -435,6 +459,14 @@ int pyh_destroy(void* ctx) {
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_dts) cudaFree(c->d_dts);
     if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
+    if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
+    if (c->ev_in_done) cudaEventDestroy(c->ev_in_done);
+    if (c->ev_in_consumed) cudaEventDestroy(c->ev_in_consumed);
+    if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
+    for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
+    if (c->d_stage_in) cudaFree(c->d_stage_in);
+    if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -474,6 +506,94 @@ int pyh_download_state(void* ctx, int gid, double* aos) {
     CU(cudaMemcpyAsync(aos, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->launches++;
+    return 0;
+}
+
+int pyh_upload_state_async(void* ctx, int gid, const double* aos) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    (void)hb;
+    if (!c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!aos) return set_err(PYH_ERR_INVALID, "null state pointer");
+    int rc = ensure_streaming(c);
+    if (rc) return rc;
+    const int idx = it_->second;
+    const size_t per = 4 * (size_t)c->lay.nx * c->lay.ny;
+    // the staging area may still be read by the conversion of the previous batch
+    CU(cudaStreamWaitEvent(c->s_in, c->ev_in_consumed, 0));
+    CU(cudaMemcpyAsync(c->d_stage_in + idx * per, aos, per * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+    c->staged[idx] = 1;
+    return 0;
+}
+
+int pyh_commit_uploads(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = ensure_streaming(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->lay.nx * c->lay.ny;
+    CU(cudaEventRecord(c->ev_in_done, c->s_in));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
+    for (size_t b = 0; b < c->blocks.size(); ++b) {
+        if (!c->staged[b]) continue;
+        k_aos_to_soa<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, c->d_stage_in + b * 4 * n, c->blocks[b].dev.base + c->po.H[c->i0]);
+        CU(cudaGetLastError());
+        c->launches++;
+        c->staged[b] = 0;
+    }
+    CU(cudaEventRecord(c->ev_in_consumed, c->stream));
+    return 0;
+}
+
+int pyh_download_state_async(void* ctx, int gid, double* aos) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!aos) return set_err(PYH_ERR_INVALID, "null state pointer");
+    int rc = ensure_streaming(c);
+    if (rc) return rc;
+    const int idx = it_->second;
+    const size_t n = (size_t)c->lay.nx * c->lay.ny;
+    double* stage = c->d_stage_out + idx * 4 * n;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_out_done[idx], 0));   // previous copy out of this block's staging area
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], stage, 4);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaEventRecord(c->ev_out_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->s_out, c->ev_out_ready, 0));
+    CU(cudaMemcpyAsync(aos, stage, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+    CU(cudaEventRecord(c->ev_out_done[idx], c->s_out));
+    return 0;
+}
+
+int pyh_transfers_sync(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return set_err(PYH_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    if (c->s_in) CU(cudaStreamSynchronize(c->s_in));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->s_out) CU(cudaStreamSynchronize(c->s_out));
+    return 0;
+}
+
+int pyh_downloads_sync(void* ctx) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return set_err(PYH_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    if (c->s_out) CU(cudaStreamSynchronize(c->s_out));
+    return 0;
+}
+
+int pyh_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_err(PYH_ERR_INVALID, "null pointer");
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_err(PYH_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+int pyh_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
     return 0;
 }
 

@@ -53,6 +53,7 @@ class Engine:
         self._ctx = C.c_void_p()
         check(self.lib.pyh_create(C.byref(cfg), C.byref(self._ctx)))
         self.gids = []
+        self._pinned = []
 
     # -- construction ---------------------------------------------------------------------------
     def add_block(self, gid, mesh, neighbors, bcs, local_gids=None, is_cartesian=None):
@@ -100,6 +101,9 @@ class Engine:
         if self._ctx:
             self.lib.pyh_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            for p in self._pinned:
+                self.lib.pyh_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -123,6 +127,42 @@ class Engine:
             raise ValueError("out must be a C-contiguous float64 array of shape (ny, nx, 4)")
         check(self.lib.pyh_download_state(self._ctx, int(gid), _dp(out)))
         return out
+
+    # -- asynchronous streaming (copy streams overlap the compute stream) ----------------------------
+    def _check_stream_buf(self, a):
+        if a.shape != (self.ny, self.nx, 4) or a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise ValueError("buffer must be a C-contiguous float64 array of shape (ny, nx, 4)")
+
+    def upload_async(self, gid, aos):
+        """Enqueue the H2D copy of a (page-locked) host state; the buffer must stay untouched until
+        ``transfers_sync``.  Takes effect at the next ``commit_uploads``."""
+        self._check_stream_buf(aos)
+        check(self.lib.pyh_upload_state_async(self._ctx, int(gid), _dp(aos)))
+
+    def commit_uploads(self):
+        check(self.lib.pyh_commit_uploads(self._ctx))
+
+    def download_async(self, gid, out):
+        """Enqueue conversion + D2H copy of the current solution of block ``gid`` into ``out``
+        (page-locked); valid after ``transfers_sync``."""
+        self._check_stream_buf(out)
+        check(self.lib.pyh_download_state_async(self._ctx, int(gid), _dp(out)))
+
+    def transfers_sync(self):
+        check(self.lib.pyh_transfers_sync(self._ctx))
+
+    def downloads_sync(self):
+        """Wait for the D2H copies enqueued so far only (safe from a writer thread)."""
+        check(self.lib.pyh_downloads_sync(self._ctx))
+
+    def pinned_state_buffer(self):
+        """A page-locked (ny, nx, 4) float64 array owned by the engine (freed in ``close``)."""
+        nbytes = self.ny * self.nx * 4 * 8
+        p = C.c_void_p()
+        check(self.lib.pyh_host_alloc(nbytes, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_double * (self.ny * self.nx * 4)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.ny, self.nx, 4)
 
     def download_ghost(self, gid, side):
         s = SIDES.index(side)

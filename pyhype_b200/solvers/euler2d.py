@@ -33,6 +33,62 @@ class _Logger:
         self._log.error(msg)
 
 
+class _AsyncSolutionWriter:
+    """``every_n_timesteps`` dumps that do not stall the device loop (solvers/base.py:158-172 layout):
+    the D2H copies run on the engine's copy-out stream into page-locked buffers while the next steps
+    compute, and ``np.save`` runs on a worker thread.  Two buffer sets; a third dump waits for the
+    first to reach the disk."""
+
+    def __init__(self, engine, gids, depth=2):
+        import queue
+        import threading
+
+        self._engine = engine
+        self._sets = [{g: engine.pinned_state_buffer() for g in gids} for _ in range(depth)]
+        self._free = queue.Queue()
+        for i in range(depth):
+            self._free.put(i)
+        self._jobs = queue.Queue()
+        self._error = None
+        self._thread = threading.Thread(target=self._work, name="pyhype_b200-writer", daemon=True)
+        self._thread.start()
+
+    def submit(self, files):
+        """files: {gid: path}; returns as soon as the copies are enqueued."""
+        self._raise_if_failed()
+        i = self._free.get()
+        for g in files:
+            self._engine.download_async(g, self._sets[i][g])
+        self._jobs.put((i, dict(files)))
+
+    def _work(self):
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            i, files = job
+            try:
+                self._engine.downloads_sync()
+                for g, f in files.items():
+                    np.save(file=f, arr=self._sets[i][g])
+            except Exception as e:  # surfaced on the solver thread by the next submit / close
+                self._error = e
+            finally:
+                self._free.put(i)
+
+    def _raise_if_failed(self):
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
+
+    def close(self):
+        if self._thread is not None:
+            self._jobs.put(None)
+            self._thread.join()
+            self._thread = None
+        self._raise_if_failed()
+
+
 def _validate(config):
     """Reject what the reference rejects, with the same exception types."""
     if config.fvm_type != "MUSCL":
@@ -122,6 +178,8 @@ class Euler2D:
             blk._attach(self._engine)
         self._engine.finalize()
         self._halo = None
+        self._writer = None
+        self._in_solve = False
         if self._world > 1:
             import torch
             import torch.distributed as dist
@@ -169,7 +227,14 @@ class Euler2D:
 
     def solve(self):
         self._pre_process_solve()
-        self._solve()
+        self._in_solve = True
+        try:
+            self._solve()
+        finally:
+            self._in_solve = False
+            if self._writer is not None:
+                self._writer.close()   # every dump is on disk when solve() returns (or raises)
+                self._writer = None
         self._post_process_solve()
 
     # -- internals ---------------------------------------------------------------------------------------
@@ -308,8 +373,14 @@ class Euler2D:
         ):
             current_path = self.write_path / str(self.num_time_step)
             current_path.mkdir(parents=True, exist_ok=True)
-            for block in self.blocks:
-                self.write_output_nodes(
-                    str(current_path / self.config.write_solution_name) + "_blk_" + str(block.global_block_num),
-                    block.state.data,
-                )
+            self._flush_host_states()
+            if self._writer is None:
+                self._writer = _AsyncSolutionWriter(self._engine, [b.global_block_num for b in self.blocks])
+            self._writer.submit({
+                block.global_block_num:
+                    str(current_path / self.config.write_solution_name) + "_blk_" + str(block.global_block_num) + ".npy"
+                for block in self.blocks
+            })
+            if not self._in_solve:   # called by user code outside solve(): behave synchronously
+                self._writer.close()
+                self._writer = None

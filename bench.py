@@ -146,7 +146,9 @@ def run_ours(args):
     if wsize > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+        from pyhype_b200.distributed import init_nccl
+
+        init_nccl(lrank)
 
     nb, n = args.blocks_per_gpu, args.block
     integ = args.integrator

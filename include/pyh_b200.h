@@ -158,6 +158,20 @@ int pyh_step_begin(void* ctx, double dt);
 int pyh_step_begin_dev(void* ctx, const double* dev_dt);
 int pyh_stage(void* ctx, int stage);
 int pyh_step(void* ctx, double dt);
+/* Overlap of the remote exchange with the stage kernel (the reference posts Isend/Irecv and only then
+ * applies local BCs, blocks/base.py:454-465; here the overlap partner is the residual itself):
+ *   pyh_unpack_halo_on(recv, stream): pyh_unpack_halo on a caller-owned stream (a cudaStream_t value, e.g.
+ *     the one the NCCL receives complete on), followed by an epoch stamp in the device control block.
+ *   pyh_stage_overlapped(s): ONE launch of the stage kernel in which the thread blocks that read remotely
+ *     owned ghost cells are dispatched last and wait (normally zero time) for the stamp of the latest
+ *     pyh_unpack_halo_on; all other thread blocks never wait.  The caller must have enqueued that unpack
+ *     (on any stream) before calling, and must not touch the ghost frames from the compute stream meanwhile.
+ *   pyh_overlap_info: whether the context has remote edges + a dispatch table, and how many thread blocks
+ *     per launch read remote ghost cells (the host falls back to the blocking order when they could fill
+ *     the device on their own). */
+int pyh_stage_overlapped(void* ctx, int stage);
+int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream);
+int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas);
 
 /* Euler2D._solve loop (pyhype/solvers/Euler2D.py:195-210), device resident: dt, t and the step
  * counter stay on the GPU; the host only polls every `poll_every` steps.  dts_out (may be NULL)

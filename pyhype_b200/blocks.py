@@ -86,6 +86,7 @@ class _GhostView:
         @property
         def data(self):
             self._block._solver._flush_host_states()
+            self._block._solver._wait_halo()   # an overlapped remote exchange may still be in flight
             return self._block._engine.download_ghost(self._block.global_block_num, self._side)
 
     def __init__(self, block):

@@ -1,4 +1,5 @@
 // pyh_api.cu -- context, memory management and the extern "C" entry points of include/pyh_b200.h
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,7 +10,7 @@
 #include <string>
 
 #include "pyh_kernels.cuh"
-#include "pyh_stage_march.cuh"
+#include "pyh_march_tu.cuh"
 
 using namespace pyh;
 
@@ -28,6 +29,15 @@ static int set_err(int code, const char* fmt, ...) {
             return set_err(PYH_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
                            cudaGetErrorString(e_));                                                  \
     } while (0)
+
+// The stage kernel is instantiated per (flux, limiter, reconstruction, quadrature points) in three translation
+// units (pyh_march_nq{1,2,3}.cu, compiled in parallel); each exports its picker.
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const unsigned*, const unsigned long long);
+namespace pyh {
+MarchFn pick_march_nq1(int f, int l, int p);
+MarchFn pick_march_nq2(int f, int l, int p);
+MarchFn pick_march_nq3(int f, int l, int p);
+}
 
 namespace {
 
@@ -71,6 +81,10 @@ struct Ctx {
     double* d_stage_in = nullptr;           // nblocks x (ny, nx, 4)
     double* d_stage_out = nullptr;
     std::vector<char> staged;
+    // overlap of the remote ghost exchange with the stage kernel (pyh_stage_overlapped)
+    unsigned* d_cta_order = nullptr;            // dispatch order: thread blocks reading remote ghost cells last
+    unsigned long long halo_epoch_issued = 0;   // stamp handed to the latest pyh_unpack_halo_on
+    int n_remote_ctas = 0;
 };
 
 int ensure_streaming(Ctx* c) {
@@ -116,29 +130,8 @@ int dalloc(HostBlock& hb, double** p, long long ndoubles, bool zero) {
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- stage kernel dispatch ------------------------------------------------------------------------
-typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int);
-template <int F, int L>
-MarchFn mpick_p(int p) { return p ? k_stage_march<F, L, 1> : k_stage_march<F, L, 0>; }
-template <int F>
-MarchFn mpick_l(int l, int p) {
-    switch (l) {
-        case 0: return mpick_p<F, 0>(p);
-        case 1: return mpick_p<F, 1>(p);
-        case 2: return mpick_p<F, 2>(p);
-        default: return mpick_p<F, 3>(p);
-    }
-}
-MarchFn pick_march(int f, int l, int p) {
-#ifdef PYH_ONLY_ROE_VENKAT_CONS   // kernel-tuning builds (tools/build_variant.sh): one instantiation, 10x faster to compile
-    (void)f; (void)l; (void)p;
-    return k_stage_march<0, 0, 0>;
-#else
-    switch (f) {
-        case 0: return mpick_l<0>(l, p);
-        case 1: return mpick_l<1>(l, p);
-        default: return mpick_l<2>(l, p);
-    }
-#endif
+MarchFn pick_march(int f, int l, int p, int nq) {
+    return nq == 1 ? pyh::pick_march_nq1(f, l, p) : (nq == 2 ? pyh::pick_march_nq2(f, l, p) : pyh::pick_march_nq3(f, l, p));
 }
 
 // lanes per CTA: two ring lanes per strip, so pick the width that wastes the fewest lanes for this nx
@@ -166,21 +159,30 @@ void choose_march_shape(Ctx* c) {
     c->march_tys = tys;
 }
 
-int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
-    MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon);
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, bool overlapped = false) {
+    const int nq = c->cfg.num_quadrature_points;
+    MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon, nq);
     const int nt = c->march_nt, tys = c->march_tys;
-    size_t smem = (size_t)MARCH_SMEM_DOUBLES_PER_THREAD * nt * sizeof(double);
+    size_t smem = (size_t)march_smem_doubles(nq) * nt * sizeof(double);
     static thread_local MarchFn configured[64];
     static thread_local int nconf = 0;
     bool done = false;
     for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
     if (!done) {
-        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_SMEM_DOUBLES_PER_THREAD * MARCH_MAX_THREADS * (int)sizeof(double)));
+        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * MARCH_MAX_THREADS * (int)sizeof(double)));
         if (const char* e = getenv("PYH_CARVEOUT")) CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         if (nconf < 64) configured[nconf++] = fn;
     }
     dim3 grid(cdiv(c->lay.nx, nt - 4), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
-    fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg);
+    static const bool force_table = getenv("PYH_FORCE_ORDER_TABLE") != nullptr;   // diagnostics
+    static const bool no_wait = getenv("PYH_NO_EPOCH_WAIT") != nullptr;
+    if ((overlapped || force_table) && c->d_cta_order) {
+        dim3 lin(grid.x * grid.y * grid.z);
+        fn<<<lin, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, c->d_cta_order,
+                                         (overlapped && !no_wait) ? c->halo_epoch_issued : 0ull);
+    } else {
+        fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, nullptr, 0ull);
+    }
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -218,14 +220,14 @@ int do_ghost(Ctx* c, int buf) {
     return 0;
 }
 
-int do_stage(Ctx* c, int s) {
+int do_stage(Ctx* c, int s, bool overlapped = false) {
     const int S = c->cfg.num_stages;
     int cur = (s == 0) ? c->i0 : c->cur;
     int next;
     if (s == S - 1) next = (S == 1) ? c->i1 : c->i0;
     else next = (cur == c->i1) ? c->i2 : c->i1;
     StagePlan p = make_plan(c, s, cur, next);
-    int rc = launch_stage(c, p, 0);
+    int rc = launch_stage(c, p, 0, overlapped);
     if (rc) return rc;
     c->cur = next;
     if (s == S - 1) {
@@ -264,7 +266,7 @@ int pyh_create(const pyh_config* cfg, void** out) {
     if (cfg->flux < 0 || cfg->flux > 2) return set_err(PYH_ERR_INVALID, "unknown flux function %d", cfg->flux);
     if (cfg->limiter < 0 || cfg->limiter > 3) return set_err(PYH_ERR_INVALID, "unknown slope limiter %d", cfg->limiter);
     if (cfg->recon < 0 || cfg->recon > 1) return set_err(PYH_ERR_INVALID, "unknown reconstruction type %d", cfg->recon);
-    if (cfg->num_quadrature_points != 1) return set_err(PYH_ERR_INVALID, "only fvm_num_quadrature_points == 1 is implemented on the device (got %d)", cfg->num_quadrature_points);
+    if (cfg->num_quadrature_points < 1 || cfg->num_quadrature_points > 3) return set_err(PYH_ERR_INVALID, "fvm_num_quadrature_points must be 1, 2 or 3 (got %d)", cfg->num_quadrature_points);
     if (cfg->num_stages < 1 || cfg->num_stages > PYH_MAX_STAGES) return set_err(PYH_ERR_INVALID, "num_stages must be in 1..%d", PYH_MAX_STAGES);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -283,6 +285,14 @@ int pyh_create(const pyh_config* cfg, void** out) {
     c->C.gm1 = cfg->gamma - 1.0;
     c->C.k = 1.0 / (cfg->gamma - 1.0);
     c->C.gm = cfg->gamma / (cfg->gamma - 1.0);
+    {   // mesh/quadratures.py:33-37, same expressions in the same (dict) order
+        const int nq = cfg->num_quadrature_points;
+        for (int q = 0; q < 3; ++q) { c->C.qw[q] = 0.0; c->C.qp[q] = 0.0; }
+        if (nq == 1) { c->C.qp[0] = 0.0; c->C.qw[0] = 2.0; }
+        else if (nq == 2) { c->C.qp[0] = -1.0 / std::sqrt(3.0); c->C.qp[1] = 1.0 / std::sqrt(3.0); c->C.qw[0] = c->C.qw[1] = 1.0; }
+        else { c->C.qp[0] = -std::sqrt(3.0 / 5.0); c->C.qp[1] = 0.0; c->C.qp[2] = std::sqrt(3.0 / 5.0);
+               c->C.qw[0] = 5.0 / 9.0; c->C.qw[1] = 8.0 / 9.0; c->C.qw[2] = 5.0 / 9.0; }
+    }
     memset(&c->tab, 0, sizeof(c->tab));
     c->tab.nstages = cfg->num_stages;
     for (int s = 0; s < cfg->num_stages; ++s)
@@ -301,7 +311,7 @@ int pyh_create(const pyh_config* cfg, void** out) {
         for (int h = 0; h < 3; ++h) { po.H[h] = (h < nH) ? n * PLn : 0; if (h < nH) n += 4; }
         for (int r = 0; r < cfg->num_stages; ++r) if (c->need_acc[r]) { po.P[r] = n * PLn; n += 4; }
         po.A = n++ * PLn;
-        po.dxy = n * PLn; n += 8;
+        po.dxy = n * PLn; n += 8 * cfg->num_quadrature_points;
         po.Lv = n++ * PLn; po.cv = n++ * PLn; po.sv = n++ * PLn;
         po.Lh = n++ * PLn; po.ch = n++ * PLn; po.sh = n++ * PLn;
         po.cdx = n++ * PLn; po.cdy = n++ * PLn;
@@ -362,7 +372,7 @@ int pyh_add_block(void* ctx, const pyh_block_desc* b) {
     if ((rc = put(b->sin_h, sh, ny + 1, nx))) return rc;
     CU(cudaMemcpyAsync(c->d_scratch, b->nodes_x, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_scratch + nn, b->nodes_y, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy);
+    k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy, c->cfg.num_quadrature_points, c->C);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     D.dbg = nullptr;
@@ -439,6 +449,30 @@ int pyh_finalize(void* ctx) {
         CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
     }
     choose_march_shape(c);
+    const char* test_table = getenv("PYH_TEST_TABLE");   // diagnostics: 1 = first/last row strips last, 2 = identity order
+    if (!c->slots.empty() || test_table) {
+        const int nt = c->march_nt, tys = c->march_tys, nx = c->lay.nx, ny = c->lay.ny;
+        const unsigned gx = cdiv(nx, nt - 4), gy = cdiv(ny, tys), gz = (unsigned)c->blocks.size();
+        if (gx <= 1024 && gy <= 1024 && gz <= 2048) {
+            std::vector<unsigned> near, far;
+            for (unsigned z = 0; z < gz; ++z)
+                for (unsigned y = 0; y < gy; ++y)
+                    for (unsigned x = 0; x < gx; ++x) {
+                        const BlkDev& D = c->blocks[z].dev;
+                        const int jhi = (int)x * (nt - 4) - 3 + nt;                       // last column a thread block reads
+                        const int ihi = std::min((int)y * tys + tys, ny) + 1;             // last row it reads
+                        bool touch = (x == 0 && D.remote_slot[PYH_WEST] >= 0) || (jhi >= nx && D.remote_slot[PYH_EAST] >= 0) ||
+                                           (y == 0 && D.remote_slot[PYH_SOUTH] >= 0) || (ihi >= ny && D.remote_slot[PYH_NORTH] >= 0);
+                        if (test_table) touch = (atoi(test_table) == 1) && (y == 0 || y == gy - 1);
+                        const unsigned code = x | (y << 10) | (z << 20);
+                        (touch ? far : near).push_back(touch ? (code | 0x80000000u) : code);
+                    }
+            c->n_remote_ctas = (int)far.size();
+            near.insert(near.end(), far.begin(), far.end());
+            CU(cudaMalloc(&c->d_cta_order, near.size() * sizeof(unsigned)));
+            CU(cudaMemcpy(c->d_cta_order, near.data(), near.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        }
+    }
     c->finalized = true;
     return 0;
 }
@@ -465,6 +499,7 @@ int pyh_destroy(void* ctx) {
     if (c->ev_in_consumed) cudaEventDestroy(c->ev_in_consumed);
     if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
     for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
+    if (c->d_cta_order) cudaFree(c->d_cta_order);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -722,6 +757,42 @@ int pyh_stage(void* ctx, int stage) {
     int rc = do_stage(c, stage);
     if (rc) return rc;
     c->stage_next = stage + 1;
+    return 0;
+}
+
+int pyh_stage_overlapped(void* ctx, int stage) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (stage != c->stage_next || stage >= c->cfg.num_stages) return set_err(PYH_ERR_STATE, "stage %d out of order (expected %d)", stage, c->stage_next);
+    if (!c->d_cta_order) return set_err(PYH_ERR_STATE, "pyh_stage_overlapped: no remote edges (or grid too large for the dispatch table)");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = do_stage(c, stage, true);
+    if (rc) return rc;
+    c->stage_next = stage + 1;
+    return 0;
+}
+
+int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (c->slots.empty()) return 0;
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+    int m = std::max(c->lay.nx, c->lay.ny);
+    dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
+    k_unpack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[c->cur], c->d_slots, dev_recv);
+    CU(cudaGetLastError());
+    k_set_halo_epoch<<<1, 1, 0, st>>>(c->d_ctl, ++c->halo_epoch_issued);
+    CU(cudaGetLastError());
+    c->launches += 2;
+    return 0;
+}
+
+int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (capable) *capable = c->d_cta_order ? 1 : 0;
+    if (n_remote_ctas) *n_remote_ctas = c->n_remote_ctas;
     return 0;
 }
 

@@ -95,6 +95,11 @@ k_unpack_halo(const BlkDev* __restrict__ blks, Layout lay, unsigned buf, const H
     dst[o] = d[0]; dst[o + lay.plane] = d[1]; dst[o + 2 * lay.plane] = d[2]; dst[o + 3 * lay.plane] = d[3];
 }
 
+__global__ void k_set_halo_epoch(Control* ctl, unsigned long long epoch) {
+    __threadfence();
+    *(volatile unsigned long long*)&ctl->halo_epoch = epoch;
+}
+
 // ------------------------------------------------------------------------------------------------
 // CFL reduction + realizability (quad_block.py:423-436, states/conservative.py:161-165)
 // ------------------------------------------------------------------------------------------------
@@ -211,7 +216,7 @@ __global__ void k_step_end(Control* ctl, double* dts, long long dts_cap) {
 __global__ void __launch_bounds__(256)
 k_geometry(Layout lay, const double* __restrict__ xn, const double* __restrict__ yn,  // (ny+1, nx+1) dense
            double* __restrict__ dxy, double* __restrict__ Lv, double* __restrict__ Lh,
-           double* __restrict__ cdx, double* __restrict__ cdy) {
+           double* __restrict__ cdx, double* __restrict__ cdy, int nq, Consts C) {
     const int nx = lay.nx, ny = lay.ny;
     long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long total = (long long)(ny + 1) * (nx + 1);
@@ -241,12 +246,17 @@ k_geometry(Layout lay, const double* __restrict__ xn, const double* __restrict__
         double yc = 0.25 * (yne + ynw + yse + ysw);
         unsigned o = lay.at(i, j);
         const size_t PL = lay.plane;
-        // quadrature point of the 1-point rule: 0.5 * ((p2 - p1) * 0 + (p2 + p1)), (p1, p2) per side
-        auto qp = [](double p1, double p2) { return 0.5 * ((p2 - p1) * 0.0 + (p2 + p1)); };
-        dxy[0 * PL + o] = qp(xne, xse) - xc; dxy[1 * PL + o] = qp(yne, yse) - yc;   // E: (NE, SE)
-        dxy[2 * PL + o] = qp(xnw, xsw) - xc; dxy[3 * PL + o] = qp(ynw, ysw) - yc;   // W: (NW, SW)
-        dxy[4 * PL + o] = qp(xne, xnw) - xc; dxy[5 * PL + o] = qp(yne, ynw) - yc;   // N: (NE, NW)
-        dxy[6 * PL + o] = qp(xse, xsw) - xc; dxy[7 * PL + o] = qp(yse, ysw) - yc;   // S: (SE, SW)
+        // quadrature points (mesh/quadratures.py:56-95): 0.5 * ((p2 - p1) * point + (p2 + p1)), (p1, p2) per side;
+        // plane ((q * 4 + f) * 2 + {x, y}) holds the offset of point q of face f from the centroid
+        for (int q = 0; q < nq; ++q) {
+            const double pt = C.qp[q];
+            auto qp = [pt](double p1, double p2) { return 0.5 * ((p2 - p1) * pt + (p2 + p1)); };
+            double* d = dxy + (size_t)(q * 8) * PL;
+            d[0 * PL + o] = qp(xne, xse) - xc; d[1 * PL + o] = qp(yne, yse) - yc;   // E: (NE, SE)
+            d[2 * PL + o] = qp(xnw, xsw) - xc; d[3 * PL + o] = qp(ynw, ysw) - yc;   // W: (NW, SW)
+            d[4 * PL + o] = qp(xne, xnw) - xc; d[5 * PL + o] = qp(yne, ynw) - yc;   // N: (NE, NW)
+            d[6 * PL + o] = qp(xse, xsw) - xc; d[7 * PL + o] = qp(yse, ysw) - yc;   // S: (SE, SW)
+        }
         // dx = E.midpoint.x - W.midpoint.x ; dy = N.midpoint.y - S.midpoint.y  (midpoint = 0.5*(high+low))
         cdx[o] = 0.5 * (xne + xse) - 0.5 * (xnw + xsw);
         cdy[o] = 0.5 * (ynw + yne) - 0.5 * (ysw + yse);

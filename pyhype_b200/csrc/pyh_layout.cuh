@@ -60,6 +60,7 @@ struct Control {
     int active;      // 1 while t < t_final
     int bad;         // unrealizable state seen
     int pad[2];
+    unsigned long long halo_epoch;   // stamp of the last remote ghost exchange that has landed (pyh_unpack_halo_on)
 };
 
 struct BlkDev {

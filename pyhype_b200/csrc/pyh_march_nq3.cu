@@ -1,0 +1,30 @@
+// Stage-kernel instantiations for fvm_num_quadrature_points == 3 (one translation unit per value so that
+// the three compile in parallel; see __graft_entry__.build).
+#include "pyh_stage_march.cuh"
+
+namespace pyh {
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const unsigned*, const unsigned long long);
+template <int F, int L>
+static MarchFn mpick_p(int p) { return p ? k_stage_march<F, L, 1, 3> : k_stage_march<F, L, 0, 3>; }
+template <int F>
+static MarchFn mpick_l(int l, int p) {
+    switch (l) {
+        case 0: return mpick_p<F, 0>(p);
+        case 1: return mpick_p<F, 1>(p);
+        case 2: return mpick_p<F, 2>(p);
+        default: return mpick_p<F, 3>(p);
+    }
+}
+MarchFn pick_march_nq3(int f, int l, int p) {
+#ifdef PYH_ONLY_ROE_VENKAT_CONS   // kernel-tuning builds (tools/build_variant.sh): one instantiation
+    (void)f; (void)l; (void)p;
+    return k_stage_march<0, 0, 0, 3>;
+#else
+    switch (f) {
+        case 0: return mpick_l<0>(l, p);
+        case 1: return mpick_l<1>(l, p);
+        default: return mpick_l<2>(l, p);
+    }
+#endif
+}
+}  // namespace pyh

@@ -29,45 +29,57 @@
 #include <type_traits>
 #include "pyh_layout.cuh"
 #include "pyh_math.cuh"
+#include "pyh_march_tu.cuh"
 
 namespace pyh {
-
-#ifndef PYH_MARCH_MAXT
-#define PYH_MARCH_MAXT 128
-#endif
-#ifndef PYH_MARCH_MINB
-#define PYH_MARCH_MINB 4
-#endif
-constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
-constexpr int MARCH_SMEM_DOUBLES_PER_THREAD = 12 + 8 + 8 + 8 + 4 + 8;   // sQ[3], sFE[2], sIW[2], sQN[2], sIS, sQW, sQS
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
-template <int FLUX, int LIM, int PRIM>
-__global__ void __launch_bounds__(MARCH_MAX_THREADS, PYH_MARCH_MINB)
+template <int FLUX, int LIM, int PRIM, int NQ>
+__global__ void __launch_bounds__(MARCH_MAX_THREADS, march_min_blocks(NQ))
 k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-              const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg) {
+              const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg,
+              const unsigned* __restrict__ cta_order, const unsigned long long wait_epoch) {
     if (!ctl->active) return;
+    // Block coordinates: (column strip, row strip, mesh block).  Plain launches use the 3-D grid.  Overlapped
+    // launches (pyh_stage_overlapped) use a 1-D grid and a host-built dispatch order in which the thread blocks
+    // that read remotely owned ghost cells come LAST: by the time they are dispatched the NCCL strip exchange
+    // running on the communication stream has normally landed; if not, they wait for its epoch stamp.
+    unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (cta_order) {
+        const unsigned code = cta_order[blockIdx.x];
+        bx = code & 0x3ffu; by = (code >> 10) & 0x3ffu; bz = (code >> 20) & 0x7ffu;
+        if ((code >> 31) && wait_epoch) {
+            if (threadIdx.x == 0) {
+                const volatile unsigned long long* ep = &ctl->halo_epoch;
+                while (*ep < wait_epoch) __nanosleep(256);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
     extern __shared__ double smem[];
     const int NT = blockDim.x;
     const int t = threadIdx.x;
-    double* const sQ = smem;                  // [3][4][NT]
-    double* const sFE = sQ + 12 * NT;         // [2][4][NT]
-    double* const sIW = sFE + 8 * NT;         // [2][4][NT]
-    double* const sQN = sIW + 8 * NT;         // [2][4][NT]
-    double* const sIS = sQN + 8 * NT;         // [4][NT]
-    double* const sQW = sIS + 4 * NT;         // [4][NT]  west-face state of (r, j), private
-    double* const sQS = sQW + 4 * NT;         // [4][NT]  south-face state of (r, j), private
+    double* const sQ = smem;                       // [3][4][NT]
+    double* const sFE = sQ + 12 * NT;              // [2][NQ][4][NT]  east-face states at the quadrature points
+    double* const sIW = sFE + 8 * NQ * NT;         // [2][4][NT]      integrated west-face fluxes
+    double* const sQN = sIW + 8 * NT;              // [2][NQ][4][NT]  north-face states
+    double* const sIS = sQN + 8 * NQ * NT;         // [4][NT]
+    double* const sQW = sIS + 4 * NT;              // [NQ][4][NT]  west-face states of (r, j), private
+    double* const sQS = sQW + 4 * NQ * NT;         // [NQ][4][NT]  south-face states of (r, j), private
 
-    const BlkDev& B = blks[blockIdx.z];
+    auto iFE = [&](int par_, int q, int k, int tt) { return ((par_ * NQ + q) * 4 + k) * NT + tt; };   // also sQN
+    auto iQW = [&](int q, int k) { return (q * 4 + k) * NT + t; };                                    // also sQS
+    const BlkDev& B = blks[bz];
     double* __restrict__ const base = B.base;
     const int bcE = B.bc[PYH_EAST], bcW = B.bc[PYH_WEST], bcN = B.bc[PYH_NORTH], bcS = B.bc[PYH_SOUTH];
     const int cart = B.cart;
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
-    const int j = (int)blockIdx.x * (NT - 4) - 2 + t;
-    const int i0 = (int)blockIdx.y * tys;
+    const int j = (int)bx * (NT - 4) - 2 + t;
+    const int i0 = (int)by * tys;
     const int i1 = min(i0 + tys, ny);
     const bool act = (j >= -1) && (j <= nx);
     const bool real = (j >= 0) && (j < nx);
@@ -147,14 +159,20 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 double ylE = LE * G[po.sv + oE], ylW = LW * (-G[po.sv + o]);
                 double ylN = LN * G[po.sh + oN], ylS = LS * (-G[po.sh + o]);
                 double Acell = G[po.A + o];
-                double dx[4], dy[4];
+                double dx[NQ][4], dy[NQ][4];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) { dx[f] = G[po.dxy + (2 * f) * PL + o]; dy[f] = G[po.dxy + (2 * f + 1) * PL + o]; }
+                for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        dx[q][f] = G[po.dxy + ((q * 4 + f) * 2) * PL + o];
+                        dy[q][f] = G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o];
+                    }
+                }
                 bool okA = true;
                 double ia = Ar<true>::rcp(Acell, okA);
                 if (!okA) ia = 1.0 / Acell;
-                // pass 1: gradient and the high-order terms of the four faces; the terms wait in this
-                // thread's own face-state slots so that no geometry is live while the limiter divides
+                // pass 1: gradient and the high-order terms of the four faces (at every quadrature point); the
+                // terms wait in this thread's own face-state slots so that no geometry is live while the limiter divides
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
@@ -163,44 +181,60 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
                     double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
                     double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
-                    sFE[(par * 4 + k) * NT + t] = gx * dx[0] + gy * dy[0];       // blocks/base.py:283-288
-                    sQW[k * NT + t] = gx * dx[1] + gy * dy[1];
-                    sQN[(par * 4 + k) * NT + t] = gx * dx[2] + gy * dy[2];
-                    sQS[k * NT + t] = gx * dx[3] + gy * dy[3];
+#pragma unroll
+                    for (int p = 0; p < NQ; ++p) {
+                        sFE[iFE(par, p, k, t)] = gx * dx[p][0] + gy * dy[p][0];       // blocks/base.py:283-288
+                        sQW[iQW(p, k)] = gx * dx[p][1] + gy * dy[p][1];
+                        sQN[iFE(par, p, k, t)] = gx * dx[p][2] + gy * dy[p][2];
+                        sQS[iQW(p, k)] = gx * dx[p][3] + gy * dy[p][3];
+                    }
                     if (want_grad_dbg && full && outcol) { B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; }
                 }
-                // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side
+                // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side;
+                // phi is the minimum over every quadrature point of every face
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
-                    double term[4], davg[4];
-                    term[0] = sFE[(par * 4 + k) * NT + t];
-                    term[1] = sQW[k * NT + t];
-                    term[2] = sQN[(par * 4 + k) * NT + t];
-                    term[3] = sQS[k * NT + t];
+                    double term[NQ][4];
                     double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
                     double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
                     double dmx = mx - q, dmn = mn - q;
+                    double phi = 0.0;
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) davg[f] = (q + term[f]) - q;      // limiters/base.py:99-102
-                    double phi;
-                    if (!limiter4_fast<LIM>(dmx, dmn, davg, phi)) limiter4_safe<LIM>(dmx, dmn, davg, phi);
-                    if (phi < 0.0) phi = 0.0;                                     // limiters/base.py:187
-                    sFE[(par * 4 + k) * NT + t] = q + phi * term[0];              // SecondOrderMUSCL.py:124-126
-                    sQW[k * NT + t] = q + phi * term[1];
-                    sQN[(par * 4 + k) * NT + t] = q + phi * term[2];
-                    sQS[k * NT + t] = q + phi * term[3];
+                    for (int p = 0; p < NQ; ++p) {
+                        double davg[4];
+                        term[p][0] = sFE[iFE(par, p, k, t)];
+                        term[p][1] = sQW[iQW(p, k)];
+                        term[p][2] = sQN[iFE(par, p, k, t)];
+                        term[p][3] = sQS[iQW(p, k)];
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) davg[f] = (q + term[p][f]) - q;   // limiters/base.py:99-102
+                        double pp;
+                        if (!limiter4_fast<LIM>(dmx, dmn, davg, pp)) limiter4_safe<LIM>(dmx, dmn, davg, pp);
+                        phi = (p == 0) ? pp : dmin2(phi, pp);
+                    }
+                    if (phi < 0.0) phi = 0.0;                                         // limiters/base.py:187
+#pragma unroll
+                    for (int p = 0; p < NQ; ++p) {
+                        sFE[iFE(par, p, k, t)] = q + phi * term[p][0];                // SecondOrderMUSCL.py:124-126
+                        sQW[iQW(p, k)] = q + phi * term[p][1];
+                        sQN[iFE(par, p, k, t)] = q + phi * term[p][2];
+                        sQS[iQW(p, k)] = q + phi * term[p][3];
+                    }
                     if (want_grad_dbg && full && outcol) B.dbgG[(8 + k) * (size_t)PL + o] = phi;
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t];
-                    sFE[(par * 4 + k) * NT + t] = q;
-                    sQN[(par * 4 + k) * NT + t] = q;
-                    sQW[k * NT + t] = q;
-                    sQS[k * NT + t] = q;
+#pragma unroll
+                    for (int p = 0; p < NQ; ++p) {
+                        sFE[iFE(par, p, k, t)] = q;
+                        sQN[iFE(par, p, k, t)] = q;
+                        sQW[iQW(p, k)] = q;
+                        sQS[iQW(p, k)] = q;
+                    }
                 }
             }
         }
@@ -210,41 +244,56 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         double IW[4] = {0.0, 0.0, 0.0, 0.0};
         if (full && doV) {
             const double cf = G[po.cv + o], sf = G[po.sv + o], Lf = G[po.Lv + o];
-            double QL0[4], QR0[4];
-            if (j > 0) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int p = 0; p < NQ; ++p) {   // one Riemann problem per quadrature point (fvm/base.py:344-351)
+                double QL0[4], QR0[4];
+                if (j > 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sFE[(par * 4 + k) * NT + t - 1];
-            } else if (bcW == PYH_BC_NONE) {
+                    for (int k = 0; k < 4; ++k) QL0[k] = sFE[iFE(par, p, k, t - 1)];
+                } else if (bcW == PYH_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sc * 4 + k) * NT + t - 1];      // ghost cell (r, -1), fvm/base.py:305-325
-            } else {
+                    for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sc * 4 + k) * NT + t - 1];      // ghost cell (r, -1), fvm/base.py:305-325
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sQW[k * NT + t];
-                apply_bc_edge(bcW, PYH_WEST, r, cf, sf, QL0);
+                    for (int k = 0; k < 4; ++k) QL0[k] = sQW[iQW(p, k)];
+                    apply_bc_edge(bcW, PYH_WEST, r, cf, sf, QL0);
+                }
+                if (j < nx) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sQW[iQW(p, k)];
+                } else if (bcE == PYH_BC_NONE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (r, nx)
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sFE[iFE(par, p, k, t - 1)];         // east-face state of cell (r, nx-1)
+                    apply_bc_edge(bcE, PYH_EAST, r, cf, sf, QR0);
+                }
+                if (!cart) { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }      // fvm/base.py:366-376
+                double Fq[4];
+                auto faceV = [&](auto tag) -> bool {
+                    constexpr bool FAST = decltype(tag)::value;
+                    bool ok = true;
+                    double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]};
+                    riemann_flux<FLUX, PRIM, FAST>(QL, QR, Fq, C, ok);
+                    if (!cart) unrot(Fq[1], Fq[2], cf, sf);                                  // fvm/base.py:388-390
+                    return ok;
+                };
+                if (!faceV(FastTag{})) faceV(SafeTag{});
+                // integrate_flux (fvm/base.py:188-190): L * (((0 + w0 F0) + w1 F1) + w2 F2); one point: w0 = 2
+                if (NQ == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) IW[k] = Lf * (2.0 * Fq[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[k] = acc[k] + C.qw[p] * Fq[k];
+                }
             }
-            if (j < nx) {
+            if (NQ > 1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sQW[k * NT + t];
-            } else if (bcE == PYH_BC_NONE) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (r, nx)
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sFE[(par * 4 + k) * NT + t - 1];    // east-face state of cell (r, nx-1)
-                apply_bc_edge(bcE, PYH_EAST, r, cf, sf, QR0);
+                for (int k = 0; k < 4; ++k) IW[k] = Lf * acc[k];
             }
-            if (!cart) { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }      // fvm/base.py:366-376
-            auto faceV = [&](auto tag) -> bool {
-                constexpr bool FAST = decltype(tag)::value;
-                bool ok = true;
-                double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]}, F[4];
-                riemann_flux<FLUX, PRIM, FAST>(QL, QR, F, C, ok);
-                if (!cart) unrot(F[1], F[2], cf, sf);                                    // fvm/base.py:388-390
-#pragma unroll
-                for (int k = 0; k < 4; ++k) IW[k] = Lf * (2.0 * F[k]);                  // integrate_flux, fvm/base.py:188-190
-                return ok;
-            };
-            if (!faceV(FastTag{})) faceV(SafeTag{});
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) sIW[(par * 4 + k) * NT + t] = IW[k];
@@ -252,43 +301,57 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
             const double cf = G[po.ch + o], sf = G[po.sh + o], Lf = G[po.Lh + o];
-            double QL0[4], QR0[4];
-            if (r > 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sQN[((par ^ 1) * 4 + k) * NT + t];
-            } else if (bcS == PYH_BC_NONE) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sm * 4 + k) * NT + t];          // ghost cell (-1, j)
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QL0[k] = sQS[k * NT + t];
-                apply_bc_edge(bcS, PYH_SOUTH, j, cf, sf, QL0);
-            }
-            if (r < ny) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sQS[k * NT + t];
-            } else if (bcN == PYH_BC_NONE) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (ny, j)
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) QR0[k] = sQN[((par ^ 1) * 4 + k) * NT + t];
-                apply_bc_edge(bcN, PYH_NORTH, j, cf, sf, QR0);
-            }
-            if (cart) { rot90(QL0[1], QL0[2]); rot90(QR0[1], QR0[2]); }                  // fvm/base.py:435-441
-            else { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }
             double IS[4];
-            auto faceH = [&](auto tag) -> bool {
-                constexpr bool FAST = decltype(tag)::value;
-                bool ok = true;
-                double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]}, F[4];
-                riemann_flux<FLUX, PRIM, FAST>(QL, QR, F, C, ok);
-                if (cart) unrot90(F[1], F[2]); else unrot(F[1], F[2], cf, sf);          // fvm/base.py:482-486
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int p = 0; p < NQ; ++p) {
+                double QL0[4], QR0[4];
+                if (r > 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) IS[k] = Lf * (2.0 * F[k]);
-                return ok;
-            };
-            if (!faceH(FastTag{})) faceH(SafeTag{});
+                    for (int k = 0; k < 4; ++k) QL0[k] = sQN[iFE(par ^ 1, p, k, t)];
+                } else if (bcS == PYH_BC_NONE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QL0[k] = sQ[(sm * 4 + k) * NT + t];          // ghost cell (-1, j)
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QL0[k] = sQS[iQW(p, k)];
+                    apply_bc_edge(bcS, PYH_SOUTH, j, cf, sf, QL0);
+                }
+                if (r < ny) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sQS[iQW(p, k)];
+                } else if (bcN == PYH_BC_NONE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sQ[(sc * 4 + k) * NT + t];          // ghost cell (ny, j)
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) QR0[k] = sQN[iFE(par ^ 1, p, k, t)];
+                    apply_bc_edge(bcN, PYH_NORTH, j, cf, sf, QR0);
+                }
+                if (cart) { rot90(QL0[1], QL0[2]); rot90(QR0[1], QR0[2]); }                  // fvm/base.py:435-441
+                else { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }
+                double Fq[4];
+                auto faceH = [&](auto tag) -> bool {
+                    constexpr bool FAST = decltype(tag)::value;
+                    bool ok = true;
+                    double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]};
+                    riemann_flux<FLUX, PRIM, FAST>(QL, QR, Fq, C, ok);
+                    if (cart) unrot90(Fq[1], Fq[2]); else unrot(Fq[1], Fq[2], cf, sf);      // fvm/base.py:482-486
+                    return ok;
+                };
+                if (!faceH(FastTag{})) faceH(SafeTag{});
+                if (NQ == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) IS[k] = Lf * (2.0 * Fq[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[k] = acc[k] + C.qw[p] * Fq[k];
+                }
+            }
+            if (NQ > 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) IS[k] = Lf * acc[k];
+            }
 
             // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
             if (r - 1 >= i0) {

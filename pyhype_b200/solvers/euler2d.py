@@ -114,10 +114,6 @@ def _validate(config):
         raise ValueError("reconstruction_type must be ConservativeState or PrimitiveState")
     if config.fvm_num_quadrature_points not in (1, 2, 3):
         raise KeyError(config.fvm_num_quadrature_points)
-    if config.fvm_num_quadrature_points != 1:
-        raise NotImplementedError(
-            "pyhype_b200: only fvm_num_quadrature_points == 1 is implemented on the GPU path (DESIGN.md, next)"
-        )
 
 
 class Euler2D:
@@ -187,7 +183,9 @@ class Euler2D:
             from ..distributed import HaloExchanger
 
             if not dist.is_initialized():
-                dist.init_process_group("nccl", device_id=torch.device("cuda", self._device))
+                from ..distributed import init_nccl
+
+                init_nccl(self._device)
             self._torch = torch
             self._stream = torch.cuda.ExternalStream(self._engine.stream(), device=torch.device("cuda", self._device))
             with torch.cuda.stream(self._stream):
@@ -241,6 +239,11 @@ class Euler2D:
     def _flush_host_states(self):
         for block in self.blocks:
             block.state.push_if_touched()
+
+    def _wait_halo(self):
+        if self._halo is not None:
+            with self._torch.cuda.stream(self._stream):
+                self._halo.wait()
 
     def _mark_device_newer(self):
         for block in self.blocks:

@@ -3,6 +3,12 @@
 Rows are lower-triangular ``a[s][k]``; the last row plays the role of the ``b`` weights.  The
 coefficients are written with the reference's own Python expressions so the doubles agree."""
 
+# Not in the reference's factory: the Heun / SSP-RK2 tableau that its README (and BASELINE.json's DMR
+# config) name.  Offered under its own key so that "RK2" keeps the reference's midpoint meaning.
+EXTRA_TABLEAUX = {
+    "SSPRK2": [[1], [0.5, 0.5]],
+}
+
 TABLEAUX = {
     "ExplicitEuler1": [[1]],
     "RK2": [[0.5], [0, 1]],  # midpoint rule (the factory has no Heun / SSP-RK2)
@@ -33,6 +39,8 @@ def get_tableau(name: str):
         # pyhype/time_marching/explicit_runge_kutta.py:114,155 read config.alpha, which is not a
         # SolverConfig slot: the reference raises AttributeError for these two names.
         raise AttributeError("'SolverConfig' object has no attribute 'alpha'")
+    if name in EXTRA_TABLEAUX:
+        return EXTRA_TABLEAUX[name]
     if name not in TABLEAUX:
         raise ValueError(f"Time marching scheme {name} is not available.")
     return TABLEAUX[name]

@@ -105,13 +105,13 @@ def build_oracle(blocks, nx, ny, ic, **kw):
 
 
 def build_engine(blocks, nx, ny, ic, flux="Roe", limiter="Venkatakrishnan", recon="conservative", integrator="RK4",
-                 CFL=0.7, device=0, local=None, states=None):
+                 CFL=0.7, device=0, local=None, states=None, nqp=1):
     from pyhype_b200.engine import Engine
     from pyhype_b200.mesh.quad_mesh import QuadMesh
     from pyhype_b200.time_marching import TABLEAUX
 
     tab = TABLEAUX[integrator] if isinstance(integrator, str) else integrator
-    eng = Engine(nx, ny, flux, limiter, recon, tab, GAMMA, CFL, device=device)
+    eng = Engine(nx, ny, flux, limiter, recon, tab, GAMMA, CFL, device=device, num_quadrature_points=nqp)
     gids = sorted(blocks) if local is None else sorted(local)
     meshes = {}
     for gid in gids:

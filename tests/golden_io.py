@@ -33,7 +33,8 @@ class Fixture:
 
     def scheme(self):
         m = self.meta
-        return dict(flux=m["flux"], limiter=m["limiter"], recon=m["recon"], integrator=m["integrator"], CFL=m["CFL"])
+        return dict(flux=m["flux"], limiter=m["limiter"], recon=m["recon"], integrator=m["integrator"], CFL=m["CFL"],
+                    nqp=m.get("nqp", 1))
 
     def __getitem__(self, key):
         return self.z[key]

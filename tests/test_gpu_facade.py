@@ -186,8 +186,19 @@ def test_unsupported_options_raise():
         Euler2D(config=em_config(fvm_flux_function_type="AUSM"), mesh_config=em_mesh())
     with pytest.raises(ValueError):
         Euler2D(config=em_config(nghost=2), mesh_config=em_mesh())
-    with pytest.raises(NotImplementedError):
-        Euler2D(config=em_config(fvm_num_quadrature_points=2), mesh_config=em_mesh())
+    with pytest.raises(KeyError):   # quadratures.py:37: _QUADS has keys 1, 2, 3
+        Euler2D(config=em_config(fvm_num_quadrature_points=4), mesh_config=em_mesh())
     with pytest.raises(KeyError):
         m = em_mesh().dict
         Euler2D(config=em_config(), mesh_config={k + 1: v for k, v in m.items()})  # 1-based ids, as in the shipped wedge example
+
+
+def test_facade_two_quadrature_points():
+    config = em_config(nx=16, ny=14, t_final=0.003, fvm_num_quadrature_points=2, initial_condition=ExplosionInitialCondition())
+    sim = Euler2D(config=config, mesh_config=em_mesh())
+    sim.solve()
+    prob = cases.build_oracle(em_mesh().dict, 16, 14, cases.explosion_ic, nqp=2)
+    t, dts = prob.run(0.0, 0.003 * 343.0)
+    assert sim.num_time_step == len(dts) and sim.t == t
+    for block in sim.blocks:
+        assert np.array_equal(block.state.data, prob.blocks[block.global_block_num].U)

@@ -9,7 +9,7 @@ import golden_io
 
 pytestmark = pytest.mark.gpu
 
-DEVICE_FIXTURES = [n for n in golden_io.names() if "nqp" not in n]
+DEVICE_FIXTURES = golden_io.names()
 
 
 def rel_linf(a, b):
@@ -102,7 +102,7 @@ def test_error_paths_raise_like_the_reference():
     with pytest.raises(ValueError):
         Engine(8, 8, "Roe", "Superbee", "conservative", TABLEAUX["RK2"], 1.4, 0.5)
     with pytest.raises(ValueError):
-        Engine(8, 8, "Roe", "Venkatakrishnan", "conservative", TABLEAUX["RK2"], 1.4, 0.5, num_quadrature_points=2)
+        Engine(8, 8, "Roe", "Venkatakrishnan", "conservative", TABLEAUX["RK2"], 1.4, 0.5, num_quadrature_points=4)
     blocks = cases.em_mesh()
     blocks[0]["BCTypeW"] = "Periodic"
     with pytest.raises(ValueError, match="has not been specialized"):

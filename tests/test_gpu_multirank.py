@@ -19,12 +19,15 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_run_matches_oracle(world):
+def test_sharded_run_matches_oracle(world, overlap):
+    """overlap=1: the NCCL exchange runs behind the stage kernel (pyh_stage_overlapped, dispatch table + epoch wait)."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "multirank_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 16 * overlap), os.path.join(ROOT, "tests", "multirank_worker.py")]
+    env = dict(os.environ, PYH_HALO_OVERLAP=str(overlap))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"MULTIRANK OK world={world}" in out.stdout

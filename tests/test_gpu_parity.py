@@ -105,3 +105,27 @@ def test_wedge_dirichlet_roe_conservative():
 def test_smooth_ic_weak_scaling_layout():
     blocks = cases.em_mesh(nbx=4, nby=2, east=5.0, north=2.5)
     compare(blocks, 48, 48, cases.smooth_ic, 8)
+
+
+@pytest.mark.parametrize("nqp", [2, 3])
+def test_quadrature_points_explosion(nqp):
+    compare(cases.em_mesh(), 37, 21, cases.explosion_ic, 5, nqp=nqp)
+
+
+@pytest.mark.parametrize("nqp", [2, 3])
+def test_quadrature_points_dmr_hlll_primitive(nqp):
+    # non-Cartesian blocks, Slipwall / OutletDirichlet edge states evaluated per quadrature point
+    compare(cases.dmr_mesh(), 30, 30, cases.dmr_ic, 8, flux="HLLL", integrator="RK2", CFL=0.4, recon="primitive", nqp=nqp)
+
+
+def test_quadrature_points_wedge_dirichlet_roe():
+    compare(cases.wedge_mesh(24), 30, 24, cases.wedge_ic, 8, flux="Roe", integrator="RK2", CFL=0.3, nqp=2)
+
+
+def test_ssp_rk2_heun_tableau_dmr():
+    """BASELINE.json's DMR config names SSP-RK2; the reference factory only has the midpoint "RK2".  The
+    tableau plumbing is generic: the Heun tableau (pyhype_b200 key "SSPRK2") against the oracle driven with
+    the same coefficients."""
+    from pyhype_b200.time_marching import get_tableau
+
+    compare(cases.dmr_mesh(), 30, 30, cases.dmr_ic, 10, flux="HLLL", integrator=get_tableau("SSPRK2"), CFL=0.4, recon="primitive")

@@ -58,6 +58,18 @@ def ws_ic(x, y, width, height):
     return np.where(inside[..., None], hi, lo)
 
 
+def ws_ic_smooth(x, y, width, height):
+    """Rounding-robust smooth field (IC-B): every face carries a genuine Riemann problem
+    (diagnostic runs with --ic smooth; the headline workload is the explosion box)."""
+    rho = 1.2 + 0.3 * np.sin(0.7 * x + 0.3) * np.cos(0.45 * y + 0.1)
+    u = 30 * np.cos(0.5 * x) * np.sin(0.35 * y + 0.2)
+    v = -25 * np.sin(0.4 * x + 0.5) * np.cos(0.3 * y)
+    p = 101325 * (1 + 0.2 * np.cos(0.6 * x - 0.2) * np.sin(0.5 * y + 0.4))
+    ek = 0.5 * rho * (u * u + v * v)
+    U = np.stack((rho, rho * u, rho * v, p / (GAMMA - 1) + ek), axis=-1)
+    return U / np.array([1.0, A_INF, A_INF, A_INF**2])
+
+
 BYTES_PER_CELL_STEP = {"RK4": 512.0, "RK2": 160.0, "ExplicitEuler1": 64.0}  # SURVEY.md section 8d
 
 
@@ -159,13 +171,13 @@ def run_ours(args):
     mine = sorted(g for g, r in owner.items() if r == rank)
     width, height = BLOCK_LEN * nb, BLOCK_LEN * n_gpus
 
-    eng = Engine(n, n, args.flux, "Venkatakrishnan", "conservative", tab, GAMMA, 0.7, device=lrank)
+    eng = Engine(n, n, args.flux, "Venkatakrishnan", args.recon, tab, GAMMA, 0.7, device=lrank)
     host_states = {}
     for gid in mine:
         b = blocks[gid]
         m = QuadMesh(n, n, NE=b["NE"], NW=b["NW"], SE=b["SE"], SW=b["SW"])
         eng.add_block(gid, m, {s: b["Neighbor" + s] for s in SIDES}, {s: b["BCType" + s] for s in SIDES}, local_gids=set(mine))
-        U = ws_ic(m.x[:, :, 0], m.y[:, :, 0], width, height)
+        U = (ws_ic_smooth if args.ic == "smooth" else ws_ic)(m.x[:, :, 0], m.y[:, :, 0], width, height)
         pinned = torch.empty((n, n, 4), dtype=torch.float64, pin_memory=True)
         pinned.numpy()[...] = U
         host_states[gid] = pinned
@@ -298,7 +310,7 @@ def run_ours(args):
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"synthetic weak-scaling explosion: {nb}x{n_gpus} blocks of {n}x{n} cells, {args.flux} + Venkatakrishnan + GreenGauss, conservative reconstruction, {integ}, CFL 0.7, reflection BCs",
+            "workload": f"synthetic weak-scaling explosion: {nb}x{n_gpus} blocks of {n}x{n} cells, {args.flux} + Venkatakrishnan + GreenGauss, {args.recon} reconstruction, {integ}, CFL 0.7, reflection BCs" + ("" if args.ic == "explosion" else f", IC {args.ic}"),
             "blocks_per_gpu": nb, "block": n, "cells_total": cells_total, "stages_per_step": nstages,
             "parallelism": f"block-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
             "l2_policy": f"inputs larger than L2 ({cells_local * 32 / 1e6:.0f} MB per state array per GPU vs 126 MB L2)",
@@ -457,6 +469,8 @@ def main():
     ap.add_argument("--blocks-per-gpu", type=int, default=8)
     ap.add_argument("--flux", default="Roe")
     ap.add_argument("--integrator", default="RK4")
+    ap.add_argument("--recon", default="conservative", choices=["conservative", "primitive"])
+    ap.add_argument("--ic", default="explosion", choices=["explosion", "smooth"], help="diagnostics; the headline workload is 'explosion'")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-block", type=int, default=192, help="block side of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

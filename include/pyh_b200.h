@@ -162,11 +162,12 @@ int pyh_step(void* ctx, double dt);
  * applies local BCs, blocks/base.py:454-465; here the overlap partner is the residual itself):
  *   pyh_unpack_halo_on(recv, stream): pyh_unpack_halo on a caller-owned stream (a cudaStream_t value, e.g.
  *     the one the NCCL receives complete on), followed by an epoch stamp in the device control block.
- *   pyh_stage_overlapped(s): ONE launch of the stage kernel in which the thread blocks that read remotely
- *     owned ghost cells are dispatched last and wait (normally zero time) for the stamp of the latest
- *     pyh_unpack_halo_on; all other thread blocks never wait.  The caller must have enqueued that unpack
- *     (on any stream) before calling, and must not touch the ghost frames from the compute stream meanwhile.
- *   pyh_overlap_info: whether the context has remote edges + a dispatch table, and how many thread blocks
+ *   pyh_stage_overlapped(s): ONE launch of the stage kernel whose row strips are the slowest dispatch
+ *     dimension with the strips on a block's south / north edge dispatched last; thread blocks that read
+ *     remotely owned ghost cells wait (normally zero time) for the stamp of the latest pyh_unpack_halo_on,
+ *     all others never wait.  The caller must have enqueued that unpack (on any stream) before calling,
+ *     and must not touch the ghost frames from the compute stream meanwhile.
+ *   pyh_overlap_info: whether the context has remote edges, and how many thread blocks
  *     per launch read remote ghost cells (the host falls back to the blocking order when they could fill
  *     the device on their own). */
 int pyh_stage_overlapped(void* ctx, int stage);

@@ -32,7 +32,7 @@ static int set_err(int code, const char* fmt, ...) {
 
 // The stage kernel is instantiated per (flux, limiter, reconstruction, quadrature points) in three translation
 // units (pyh_march_nq{1,2,3}.cu, compiled in parallel); each exports its picker.
-typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const unsigned*, const unsigned long long);
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const int, const unsigned long long);
 namespace pyh {
 MarchFn pick_march_nq1(int f, int l, int p);
 MarchFn pick_march_nq2(int f, int l, int p);
@@ -82,7 +82,7 @@ struct Ctx {
     double* d_stage_out = nullptr;
     std::vector<char> staged;
     // overlap of the remote ghost exchange with the stage kernel (pyh_stage_overlapped)
-    unsigned* d_cta_order = nullptr;            // dispatch order: thread blocks reading remote ghost cells last
+    bool overlap_capable = false;
     unsigned long long halo_epoch_issued = 0;   // stamp handed to the latest pyh_unpack_halo_on
     int n_remote_ctas = 0;
 };
@@ -174,14 +174,12 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, bool overlapp
         if (nconf < 64) configured[nconf++] = fn;
     }
     dim3 grid(cdiv(c->lay.nx, nt - 4), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
-    static const bool force_table = getenv("PYH_FORCE_ORDER_TABLE") != nullptr;   // diagnostics
-    static const bool no_wait = getenv("PYH_NO_EPOCH_WAIT") != nullptr;
-    if ((overlapped || force_table) && c->d_cta_order) {
-        dim3 lin(grid.x * grid.y * grid.z);
-        fn<<<lin, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, c->d_cta_order,
-                                         (overlapped && !no_wait) ? c->halo_epoch_issued : 0ull);
+    static const bool no_wait = getenv("PYH_NO_EPOCH_WAIT") != nullptr;   // diagnostics
+    if (overlapped) {
+        dim3 g2(grid.x, grid.z, grid.y);   // row strips slowest, edge strips last (see the kernel)
+        fn<<<g2, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, 1, no_wait ? 0ull : c->halo_epoch_issued);
     } else {
-        fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, nullptr, 0ull);
+        fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, 0, 0ull);
     }
     CU(cudaGetLastError());
     c->launches++;
@@ -449,29 +447,21 @@ int pyh_finalize(void* ctx) {
         CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
     }
     choose_march_shape(c);
-    const char* test_table = getenv("PYH_TEST_TABLE");   // diagnostics: 1 = first/last row strips last, 2 = identity order
-    if (!c->slots.empty() || test_table) {
+    if (!c->slots.empty()) {   // thread blocks per launch that read remotely owned ghost cells (pyh_overlap_info)
         const int nt = c->march_nt, tys = c->march_tys, nx = c->lay.nx, ny = c->lay.ny;
         const unsigned gx = cdiv(nx, nt - 4), gy = cdiv(ny, tys), gz = (unsigned)c->blocks.size();
-        if (gx <= 1024 && gy <= 1024 && gz <= 2048) {
-            std::vector<unsigned> near, far;
-            for (unsigned z = 0; z < gz; ++z)
-                for (unsigned y = 0; y < gy; ++y)
-                    for (unsigned x = 0; x < gx; ++x) {
-                        const BlkDev& D = c->blocks[z].dev;
-                        const int jhi = (int)x * (nt - 4) - 3 + nt;                       // last column a thread block reads
-                        const int ihi = std::min((int)y * tys + tys, ny) + 1;             // last row it reads
-                        bool touch = (x == 0 && D.remote_slot[PYH_WEST] >= 0) || (jhi >= nx && D.remote_slot[PYH_EAST] >= 0) ||
-                                           (y == 0 && D.remote_slot[PYH_SOUTH] >= 0) || (ihi >= ny && D.remote_slot[PYH_NORTH] >= 0);
-                        if (test_table) touch = (atoi(test_table) == 1) && (y == 0 || y == gy - 1);
-                        const unsigned code = x | (y << 10) | (z << 20);
-                        (touch ? far : near).push_back(touch ? (code | 0x80000000u) : code);
-                    }
-            c->n_remote_ctas = (int)far.size();
-            near.insert(near.end(), far.begin(), far.end());
-            CU(cudaMalloc(&c->d_cta_order, near.size() * sizeof(unsigned)));
-            CU(cudaMemcpy(c->d_cta_order, near.data(), near.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-        }
+        int n = 0;
+        for (unsigned z = 0; z < gz; ++z)
+            for (unsigned y = 0; y < gy; ++y)
+                for (unsigned x = 0; x < gx; ++x) {
+                    const BlkDev& D = c->blocks[z].dev;
+                    const int jhi = (int)x * (nt - 4) - 3 + nt;
+                    const int ihi = std::min((int)y * tys + tys, ny) + 1;
+                    n += ((x == 0 && D.remote_slot[PYH_WEST] >= 0) || (jhi >= nx && D.remote_slot[PYH_EAST] >= 0) ||
+                          (y == 0 && D.remote_slot[PYH_SOUTH] >= 0) || (ihi >= ny && D.remote_slot[PYH_NORTH] >= 0)) ? 1 : 0;
+                }
+        c->n_remote_ctas = n;
+        c->overlap_capable = gz <= 65535 && gy <= 65535;
     }
     c->finalized = true;
     return 0;
@@ -499,7 +489,6 @@ int pyh_destroy(void* ctx) {
     if (c->ev_in_consumed) cudaEventDestroy(c->ev_in_consumed);
     if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
     for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
-    if (c->d_cta_order) cudaFree(c->d_cta_order);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -764,7 +753,7 @@ int pyh_stage_overlapped(void* ctx, int stage) {
     Ctx* c = as_ctx(ctx);
     if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
     if (stage != c->stage_next || stage >= c->cfg.num_stages) return set_err(PYH_ERR_STATE, "stage %d out of order (expected %d)", stage, c->stage_next);
-    if (!c->d_cta_order) return set_err(PYH_ERR_STATE, "pyh_stage_overlapped: no remote edges (or grid too large for the dispatch table)");
+    if (!c->overlap_capable) return set_err(PYH_ERR_STATE, "pyh_stage_overlapped: context has no remote edges");
     CU(cudaSetDevice(c->cfg.device));
     int rc = do_stage(c, stage, true);
     if (rc) return rc;
@@ -791,7 +780,7 @@ int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream) {
 int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas) {
     Ctx* c = as_ctx(ctx);
     if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
-    if (capable) *capable = c->d_cta_order ? 1 : 0;
+    if (capable) *capable = c->overlap_capable ? 1 : 0;
     if (n_remote_ctas) *n_remote_ctas = c->n_remote_ctas;
     return 0;
 }

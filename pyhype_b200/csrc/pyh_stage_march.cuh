@@ -40,17 +40,23 @@ template <int FLUX, int LIM, int PRIM, int NQ>
 __global__ void __launch_bounds__(MARCH_MAX_THREADS, march_min_blocks(NQ))
 k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
               const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg,
-              const unsigned* __restrict__ cta_order, const unsigned long long wait_epoch) {
+              const int order_mode, const unsigned long long wait_epoch) {
     if (!ctl->active) return;
-    // Block coordinates: (column strip, row strip, mesh block).  Plain launches use the 3-D grid.  Overlapped
-    // launches (pyh_stage_overlapped) use a 1-D grid and a host-built dispatch order in which the thread blocks
-    // that read remotely owned ghost cells come LAST: by the time they are dispatched the NCCL strip exchange
-    // running on the communication stream has normally landed; if not, they wait for its epoch stamp.
-    unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-    if (cta_order) {
-        const unsigned code = cta_order[blockIdx.x];
-        bx = code & 0x3ffu; by = (code >> 10) & 0x3ffu; bz = (code >> 20) & 0x7ffu;
-        if ((code >> 31) && wait_epoch) {
+    // Block coordinates: (column strip, row strip, mesh block).  Plain launches: grid = (strips x, strips y, blocks).
+    // Overlapped launches (pyh_stage_overlapped): grid = (strips x, blocks, strips y) with the row-strip index
+    // rotated by one, i.e. row strips are the slowest dispatch dimension and the two that touch a block's south /
+    // north edge are dispatched LAST; by then the NCCL strip exchange running on the communication stream has
+    // normally landed.  Thread blocks that read remotely owned ghost cells wait for its epoch stamp.
+    const unsigned bx = blockIdx.x;
+    const unsigned by = order_mode ? (blockIdx.z + 1u) % gridDim.z : blockIdx.y;
+    const unsigned bz = order_mode ? blockIdx.y : blockIdx.z;
+    if (wait_epoch) {
+        const BlkDev& Bp = blks[bz];
+        const int jhi = (int)bx * ((int)blockDim.x - 4) - 3 + (int)blockDim.x;    // last column this thread block reads
+        const int ihi = min((int)by * tys + tys, lay.ny) + 1;                     // last row it reads
+        const bool touch = (bx == 0 && Bp.remote_slot[PYH_WEST] >= 0) || (jhi >= lay.nx && Bp.remote_slot[PYH_EAST] >= 0) ||
+                           (by == 0 && Bp.remote_slot[PYH_SOUTH] >= 0) || (ihi >= lay.ny && Bp.remote_slot[PYH_NORTH] >= 0);
+        if (touch) {
             if (threadIdx.x == 0) {
                 const volatile unsigned long long* ep = &ctl->halo_epoch;
                 while (*ep < wait_epoch) __nanosleep(256);

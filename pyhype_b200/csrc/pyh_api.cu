@@ -83,6 +83,11 @@ struct Ctx {
     std::vector<char> staged;
     // overlap of the remote ghost exchange with the stage kernel (pyh_stage_overlapped)
     bool overlap_capable = false;
+    // pyh_run: one period of the time loop (1 step, or 2 for single-stage tableaux whose buffers alternate)
+    // captured once as a CUDA graph and replayed
+    cudaGraphExec_t run_graph = nullptr;
+    int run_graph_steps = 0;
+    long long run_graph_launches = 0;
     unsigned long long halo_epoch_issued = 0;   // stamp handed to the latest pyh_unpack_halo_on
     int n_remote_ctas = 0;
 };
@@ -489,6 +494,7 @@ int pyh_destroy(void* ctx) {
     if (c->ev_in_consumed) cudaEventDestroy(c->ev_in_consumed);
     if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
     for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
+    if (c->run_graph) cudaGraphExecDestroy(c->run_graph);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -818,24 +824,57 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     Control h;
     memset(&h, 0, sizeof(h));
     h.t = *t_inout; h.t_final = t_final; h.dtmin_bits = DKEY_INF; h.active = 1; h.nsteps = 0; h.bad = 0;
-    CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     double* ddts = (dts_out && dts_cap > 0) ? c->d_dts : nullptr;
-    int64_t issued = 0;
+    h.dts = ddts; h.dts_cap = ddts ? dts_cap : 0;
+    CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     int rc;
+    // one time step: CFL reduction, dt, stages + ghost refresh, t += dt; every kernel early-exits once t >= t_final
+    auto enqueue_step = [&]() -> int {
+        int r;
+        if ((r = launch_dt(c, c->i0, 1))) return r;
+        k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 0, nullptr);
+        CU(cudaGetLastError());
+        for (int s = 0; s < c->cfg.num_stages; ++s) {
+            if ((r = do_stage(c, s))) return r;
+            if ((r = do_ghost(c, c->cur))) return r;
+        }
+        k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl);
+        CU(cudaGetLastError());
+        c->launches += 2;
+        return 0;
+    };
+    static const bool no_graph = getenv("PYH_NO_GRAPH") != nullptr;
+    const int period = (c->cfg.num_stages == 1) ? 2 : 1;   // steps after which the buffer roles repeat
+    if (!no_graph && !c->run_graph && max_steps >= 2 * period) {
+        // first steps run eagerly (also configures the kernels' attributes), then one period is captured
+        for (int n = 0; n < period; ++n) if ((rc = enqueue_step())) return rc;
+        const long long l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int n = 0; n < period; ++n) {
+            if ((rc = enqueue_step())) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); return rc; }
+        }
+        CU(cudaStreamEndCapture(c->stream, &g));
+        c->run_graph_launches = c->launches - l0;
+        c->launches = l0;   // nothing of the captured period has run yet
+        cudaError_t e = cudaGraphInstantiate(&c->run_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return set_err(PYH_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        c->run_graph_steps = period;
+        max_steps -= period;   // the eager steps count
+        if (steps_done) *steps_done = 0;
+    }
+    int64_t issued = 0;
     while (issued < max_steps) {
         int64_t chunk = std::min<int64_t>(poll_every, max_steps - issued);
-        for (int64_t n = 0; n < chunk; ++n) {
-            if ((rc = launch_dt(c, c->i0, 1))) return rc;
-            k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 0, nullptr);
-            CU(cudaGetLastError());
-            for (int s = 0; s < c->cfg.num_stages; ++s) {
-                if ((rc = do_stage(c, s))) return rc;
-                if ((rc = do_ghost(c, c->cur))) return rc;
+        int64_t n = 0;
+        if (c->run_graph && !no_graph) {
+            for (; n + c->run_graph_steps <= chunk; n += c->run_graph_steps) {
+                CU(cudaGraphLaunch(c->run_graph, c->stream));
+                c->launches += c->run_graph_launches;
             }
-            k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl, ddts, ddts ? dts_cap : 0);
-            CU(cudaGetLastError());
-            c->launches += 2;
         }
+        for (; n < chunk; ++n) if ((rc = enqueue_step())) return rc;
         issued += chunk;
         CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));

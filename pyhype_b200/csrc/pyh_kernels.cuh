@@ -202,9 +202,9 @@ __global__ void k_set_dt(Control* ctl, double dt_host, const double* dt_dev, Tab
             ctl->coef[s * PYH_MAX_STAGES + k] = dt * tab.a[s * PYH_MAX_STAGES + k];
 }
 
-__global__ void k_step_end(Control* ctl, double* dts, long long dts_cap) {
+__global__ void k_step_end(Control* ctl) {
     if (!ctl->active) return;
-    if (dts && ctl->nsteps < dts_cap) dts[ctl->nsteps] = ctl->dt;
+    if (ctl->dts && ctl->nsteps < ctl->dts_cap) ctl->dts[ctl->nsteps] = ctl->dt;
     ctl->t += ctl->dt;                               // Euler2D.py:209-210
     ctl->nsteps += 1;
 }

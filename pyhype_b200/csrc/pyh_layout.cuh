@@ -61,6 +61,8 @@ struct Control {
     int bad;         // unrealizable state seen
     int pad[2];
     unsigned long long halo_epoch;   // stamp of the last remote ghost exchange that has landed (pyh_unpack_halo_on)
+    double* dts;                     // pyh_run: optional per-step dt record (device), dts_cap entries
+    long long dts_cap;
 };
 
 struct BlkDev {

@@ -18,7 +18,12 @@ static MarchFn mpick_l(int l, int p) {
 MarchFn pick_march_nq2(int f, int l, int p) {
 #ifdef PYH_ONLY_ROE_VENKAT_CONS   // kernel-tuning builds (tools/build_variant.sh): one instantiation
     (void)f; (void)l; (void)p;
-    return k_stage_march<0, 0, 0, 2>;
+#ifndef PYH_ONLY_F
+#define PYH_ONLY_F 0
+#define PYH_ONLY_L 0
+#define PYH_ONLY_P 0
+#endif
+    return k_stage_march<PYH_ONLY_F, PYH_ONLY_L, PYH_ONLY_P, 2>;
 #else
     switch (f) {
         case 0: return mpick_l<0>(l, p);

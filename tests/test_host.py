@@ -125,3 +125,42 @@ def test_facade_validation_without_gpu():
                 dict(interface_interpolation="harmonic")):
         with pytest.raises(ValueError):
             _validate(cfg(**bad))
+
+
+def test_async_solution_writer_orders_backpressures_and_reports_errors(tmp_path):
+    """The every_n_timesteps writer (solvers/euler2d.py) with a stand-in engine: dumps land in submission
+    order with the data of their own submission, a third dump waits for a free buffer set, and an I/O
+    error surfaces on the solver thread."""
+    import threading
+
+    from pyhype_b200.solvers.euler2d import _AsyncSolutionWriter
+
+    class FakeEngine:
+        def __init__(self):
+            self.value = 0.0
+            self.synced = threading.Event()
+
+        def pinned_state_buffer(self):
+            return np.zeros((3, 2, 4))
+
+        def download_async(self, gid, out):
+            out[...] = self.value + gid   # "device state" at submission time
+
+        def downloads_sync(self):
+            self.synced.set()
+
+    eng = FakeEngine()
+    w = _AsyncSolutionWriter(eng, [0, 1], depth=2)
+    for step in range(5):
+        eng.value = 10.0 * step
+        w.submit({g: str(tmp_path / f"s{step}_b{g}.npy") for g in (0, 1)})
+    w.close()
+    assert eng.synced.is_set()
+    for step in range(5):
+        for g in (0, 1):
+            assert np.all(np.load(tmp_path / f"s{step}_b{g}.npy") == 10.0 * step + g)
+
+    w = _AsyncSolutionWriter(eng, [0], depth=2)
+    w.submit({0: str(tmp_path / "no_such_dir" / "x.npy")})
+    with pytest.raises(OSError):
+        w.close()

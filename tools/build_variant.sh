@@ -11,4 +11,4 @@ nvcc -shared -Xcompiler -fPIC -std=c++17 -gencode arch=compute_100a,code=sm_100a
   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -DPYH_ONLY_ROE_VENKAT_CONS "$@" \
   -I include -o gpurun_variants/libpyh_${name}.so pyhype_b200/csrc/pyh_api.cu pyhype_b200/csrc/pyh_march_nq1.cu \
   pyhype_b200/csrc/pyh_march_nq2.cu pyhype_b200/csrc/pyh_march_nq3.cu
-cuobjdump -res-usage gpurun_variants/libpyh_${name}.so 2>/dev/null | grep -A1 "k_stage_marchILi0ELi0ELi0" | grep REG
+cuobjdump -res-usage gpurun_variants/libpyh_${name}.so 2>/dev/null | grep -A1 "k_stage_marchILi[0-9]ELi[0-9]ELi[0-9]ELi1" | grep REG

@@ -282,6 +282,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     constexpr bool FAST = decltype(tag)::value;
                     bool ok = true;
                     double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]};
+#if PYH_COLD_SAFE
+                    if (!FAST) {
+                        const Flux4 fc = riemann_flux_cold<FLUX, PRIM>(QL[0], QL[1], QL[2], QL[3], QR[0], QR[1], QR[2], QR[3], C);
+                        Fq[0] = fc.f[0]; Fq[1] = fc.f[1]; Fq[2] = fc.f[2]; Fq[3] = fc.f[3];
+                    } else
+#endif
                     riemann_flux<FLUX, PRIM, FAST>(QL, QR, Fq, C, ok);
                     if (!cart) unrot(Fq[1], Fq[2], cf, sf);                                  // fvm/base.py:388-390
                     return ok;
@@ -341,6 +347,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     constexpr bool FAST = decltype(tag)::value;
                     bool ok = true;
                     double QL[4] = {QL0[0], QL0[1], QL0[2], QL0[3]}, QR[4] = {QR0[0], QR0[1], QR0[2], QR0[3]};
+#if PYH_COLD_SAFE
+                    if (!FAST) {
+                        const Flux4 fc = riemann_flux_cold<FLUX, PRIM>(QL[0], QL[1], QL[2], QL[3], QR[0], QR[1], QR[2], QR[3], C);
+                        Fq[0] = fc.f[0]; Fq[1] = fc.f[1]; Fq[2] = fc.f[2]; Fq[3] = fc.f[3];
+                    } else
+#endif
                     riemann_flux<FLUX, PRIM, FAST>(QL, QR, Fq, C, ok);
                     if (cart) unrot90(Fq[1], Fq[2]); else unrot(Fq[1], Fq[2], cf, sf);      // fvm/base.py:482-486
                     return ok;

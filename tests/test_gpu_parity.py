@@ -129,3 +129,16 @@ def test_ssp_rk2_heun_tableau_dmr():
     from pyhype_b200.time_marching import get_tableau
 
     compare(cases.dmr_mesh(), 30, 30, cases.dmr_ic, 10, flux="HLLL", integrator=get_tableau("SSPRK2"), CFL=0.4, recon="primitive")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(flux="HLLL", recon="primitive", integrator="RK2"), dict(flux="HLLE", integrator="RK2")],
+                         ids=["roe_cons", "hlll_prim", "hlle_cons"])
+def test_plain_operator_fallbacks_on_huge_magnitudes(kw):
+    """Every fast division / square-root / norm sequence has a validity range ([2^-255, 2^257), [2^-127, 2^127) for
+    the HLLL norm); outside it a phase is re-evaluated with the plain IEEE operators / the integer norm.  Scaling
+    the explosion state by 2^300 (density, momentum and energy alike: same velocities, same dt) drives EVERY
+    phase of EVERY cell through those fallbacks; the result must still equal the oracle's bit for bit.  (Scaling
+    DOWN is not an option: the reference's Roe shear wave strength lacks its factor rho -- SURVEY.md 8A.6 -- so the
+    scheme is not homogeneous in the density and blows up for small densities, in the reference as well.)"""
+    s = 2.0 ** 300
+    compare(cases.em_mesh(), 20, 20, lambda x, y: cases.explosion_ic(x, y) * s, 3, **kw)

@@ -65,7 +65,7 @@ typedef struct {
     int32_t flux;               /* pyh_flux */
     int32_t limiter;            /* pyh_limiter */
     int32_t recon;              /* pyh_recon */
-    int32_t num_quadrature_points; /* only 1 is implemented on the device */
+    int32_t num_quadrature_points; /* fvm_num_quadrature_points: 1, 2 or 3 (mesh/quadratures.py:33-37) */
     int32_t num_stages;         /* 1..PYH_MAX_STAGES */
     int32_t reserved;
     double  tableau[PYH_MAX_STAGES * PYH_MAX_STAGES]; /* a[s][k] at [s*PYH_MAX_STAGES+k], k<=s */

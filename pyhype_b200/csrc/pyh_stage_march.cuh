@@ -33,6 +33,10 @@
 
 namespace pyh {
 
+#ifndef PYH_PAIR_BARRIER
+#define PYH_PAIR_BARRIER 0
+#endif
+
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
@@ -244,7 +248,20 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 }
             }
         }
+#if PYH_PAIR_BARRIER
+        // Only lanes next to a warp boundary exchange data with another warp (east-face states, west-face fluxes, the
+        // state ring at t +- 1), so each warp synchronises with its LEFT and its RIGHT neighbour only (named barriers
+        // of 64 threads) instead of the whole CTA: adjacent warps stay within one row of each other -- which is all
+        // the double-buffered rings need -- while the CTA as a whole may spread over several rows, so one warp waiting
+        // for memory no longer stalls the other three.
+        {
+            const int w = t >> 5, nw = NT >> 5;
+            if (w > 0) asm volatile("bar.sync %0, 64;" ::"r"(w) : "memory");
+            if (w < nw - 1) asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+        }
+#else
         __syncthreads();
+#endif
 
         // ---- C(r): west face J = j of row r ----------------------------------------------------------
         double IW[4] = {0.0, 0.0, 0.0, 0.0};

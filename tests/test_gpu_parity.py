@@ -142,3 +142,9 @@ def test_plain_operator_fallbacks_on_huge_magnitudes(kw):
     scheme is not homogeneous in the density and blows up for small densities, in the reference as well.)"""
     s = 2.0 ** 300
     compare(cases.em_mesh(), 20, 20, lambda x, y: cases.explosion_ic(x, y) * s, 3, **kw)
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 1), (1, 3), (3, 2), (5, 4)])
+def test_tiny_blocks(nx, ny):
+    """blocks of a handful of cells: every cell touches two or more block edges, strips are almost all halo"""
+    compare(cases.em_mesh(), nx, ny, cases.explosion_ic, 3)

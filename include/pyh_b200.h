@@ -105,6 +105,10 @@ int pyh_destroy(void* ctx);
 /* block.state.data setter / getter (pyhype/states/base.py:84-90) */
 int pyh_upload_state(void* ctx, int gid, const double* aos);
 int pyh_download_state(void* ctx, int gid, double* aos);
+/* Uniform initial state without an upload (initial_conditions/supersonic_flood.py:50-59 assigns a (1, 1, 4)
+ * state that the setter broadcasts over the block, states/base.py:99-107): every interior cell of block gid is
+ * set to the conservative 4-vector `state`. */
+int pyh_fill_uniform(void* ctx, int gid, const double* state);
 /* Asynchronous variants for streaming use (replaces nothing in the reference, which keeps state on the
  * host; serves Solver.write_solution, pyhype/solvers/base.py:158-172, without stalling the time loop,
  * and back-to-back independent runs).  Host buffers should be page-locked; they are read / written

@@ -64,6 +64,7 @@ SIGNATURES = {
     "pyh_destroy": (C.c_int, [_vp]),
     "pyh_upload_state": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_download_state": (C.c_int, [_vp, C.c_int, c_double_p]),
+    "pyh_fill_uniform": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_upload_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_commit_uploads": (C.c_int, [_vp]),
     "pyh_download_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),

@@ -24,13 +24,21 @@ class DeviceBackedState(ConservativeState):
         self._sync = sync
         self._device_newer = False
         self._host_touched = True
+        self._uniform = None   # pending (4,) state assigned as a (1, 1, 4) array: filled on the device, no upload
         super().__init__(fluid=fluid, shape=shape)
+
+    def _materialize_uniform(self):
+        if self._uniform is not None:
+            self._data[:, :, :] = self._uniform.reshape(1, 1, 4)   # the reference's broadcast (states/base.py:99-107)
+            self._uniform = None
 
     @property
     def data(self):
         if self._device_newer:
             self._data = self._sync.download()
             self._device_newer = False
+            self._uniform = None
+        self._materialize_uniform()
         self._host_touched = True
         return self._data
 
@@ -45,15 +53,33 @@ class DeviceBackedState(ConservativeState):
             raise TypeError(f"Input array must be a Numpy array, but it is a {type(array)}.")
         if array.ndim != 3 or array.shape[-1] != 4:
             raise ValueError("Array must have 3 dims and a depth of 4.")
+        self._uniform = None
         if self._data is None or self._data.shape == array.shape:
             self._data = array
+        elif array.shape == (1, 1, 4):
+            # built-in flood initial conditions (initial_conditions/supersonic_flood.py:50-59): keep the 4 numbers,
+            # broadcast lazily on the host and by a fill kernel on the device
+            self._uniform = np.array(array, dtype=np.float64).reshape(4)
         else:
             self._data[:, :, :] = array
         self.cache.clear()
 
+    def make_non_dimensional(self):
+        if self._uniform is not None and not self._device_newer:
+            ff = self.fluid.far_field   # same divisions, on the 4 numbers instead of every cell (states/base.py:93-97)
+            self._uniform[0] /= ff.rho
+            self._uniform[1] /= ff.rho * ff.a
+            self._uniform[2] /= ff.rho * ff.a
+            self._uniform[3] /= ff.rho * ff.a**2
+            return
+        super().make_non_dimensional()
+
     def push_if_touched(self):
         if self._host_touched and not self._device_newer:
-            self._sync.upload(np.ascontiguousarray(self._data, dtype=np.float64))
+            if self._uniform is not None:
+                self._sync.fill_uniform(self._uniform)
+            else:
+                self._sync.upload(np.ascontiguousarray(self._data, dtype=np.float64))
         self._host_touched = False
 
     def mark_device_newer(self):
@@ -70,6 +96,9 @@ class _Sync:
 
     def download(self):
         return self.engine.download(self.gid)
+
+    def fill_uniform(self, state):
+        self.engine.fill_uniform(self.gid, state)
 
 
 class _GhostView:

@@ -539,6 +539,17 @@ int pyh_download_state(void* ctx, int gid, double* aos) {
     return 0;
 }
 
+int pyh_fill_uniform(void* ctx, int gid, const double* state) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!state) return set_err(PYH_ERR_INVALID, "null state pointer");
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    k_fill_uniform<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], state[0], state[1], state[2], state[3]);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 int pyh_upload_state_async(void* ctx, int gid, const double* aos) {
     Ctx* c = as_ctx(ctx);
     GET_BLOCK(c, gid, hb);

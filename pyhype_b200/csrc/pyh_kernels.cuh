@@ -283,6 +283,16 @@ k_soa_to_aos(Layout lay, const double* __restrict__ soa, double* __restrict__ ao
     unsigned o = lay.at(i, j);
     for (int k = 0; k < nplanes; ++k) aos[(long long)nplanes * n + k] = soa[k * (size_t)lay.plane + o];
 }
+__global__ void __launch_bounds__(256)
+k_fill_uniform(Layout lay, double* __restrict__ soa, double u0, double u1, double u2, double u3) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = (long long)lay.nx * lay.ny;
+    if (n >= total) return;
+    int i = (int)(n / lay.nx), j = (int)(n - (long long)i * lay.nx);
+    unsigned o = lay.at(i, j);
+    const size_t PL = lay.plane;
+    soa[o] = u0; soa[PL + o] = u1; soa[2 * PL + o] = u2; soa[3 * PL + o] = u3;
+}
 // dense (rows, cols) host-layout array -> plane
 __global__ void __launch_bounds__(256)
 k_dense_to_plane(Layout lay, const double* __restrict__ dense, double* __restrict__ plane, int rows, int cols) {

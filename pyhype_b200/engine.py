@@ -118,6 +118,11 @@ class Engine:
             raise ValueError(f"state must have shape {(self.ny, self.nx, 4)}, got {a.shape}")
         check(self.lib.pyh_upload_state(self._ctx, int(gid), _dp(a)))
 
+    def fill_uniform(self, gid, state):
+        """Set every interior cell of block ``gid`` to the conservative 4-vector ``state`` (no upload)."""
+        v = _c(np.asarray(state, dtype=np.float64).reshape(4))
+        check(self.lib.pyh_fill_uniform(self._ctx, int(gid), _dp(v)))
+
     def download(self, gid, out=None):
         """Conservative state of block ``gid`` as (ny, nx, 4); ``out`` may be a caller-owned
         (e.g. pinned) C-contiguous float64 array to receive it without an extra copy."""

@@ -143,8 +143,17 @@ class Euler2D:
         mine = [g for g, r in owner.items() if r == self.cpu]
         self._owner = owner
         self._blocks = {}
-        for g in mine:
-            self._blocks[g] = QuadBlock(config, mesh_info[g], self)  # KeyError like the reference if ids are not 0..N-1
+        inputs = {g: mesh_info[g] for g in mine}  # KeyError like the reference if ids are not 0..N-1
+        if len(mine) > 1 and config.nx * config.ny >= 1 << 18:
+            # host geometry (linspace, arctan, arccos: 1.5 s per 2048^2 block) is numpy-bound and releases the GIL
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(8, len(mine))) as pool:
+                built = list(pool.map(lambda g: QuadBlock(config, inputs[g], self), mine))
+            self._blocks = dict(zip(mine, built))
+        else:
+            for g in mine:
+                self._blocks[g] = QuadBlock(config, inputs[g], self)
 
         recon = "primitive" if config.reconstruction_type is PrimitiveState else "conservative"
         self._device = local_rank if device is None else device

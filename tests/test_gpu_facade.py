@@ -202,3 +202,38 @@ def test_facade_two_quadrature_points():
     assert sim.num_time_step == len(dts) and sim.t == t
     for block in sim.blocks:
         assert np.array_equal(block.state.data, prob.blocks[block.global_block_num].U)
+
+
+def test_builtin_flood_initial_condition_is_filled_on_the_device():
+    """SupersonicFloodInitialCondition assigns a (1, 1, 4) state that the setter broadcasts
+    (initial_conditions/supersonic_flood.py:50-59): here it becomes a fill kernel, with the same values."""
+    from pyhype_b200.initial_conditions import SupersonicFloodInitialCondition
+
+    def mesh():
+        return RectagularMeshGenerator.generate(
+            BCE=["OutletDirichlet"], BCW=["OutletDirichlet"], BCN=["OutletDirichlet"], BCS=["OutletDirichlet"],
+            east=10.0, west=0.0, north=20.0, south=0.0, n_blocks_horizontal=2, n_blocks_vertical=4)
+
+    fluid = Air(a_inf=343.0, rho_inf=1.0)
+    ic = SupersonicFloodInitialCondition(fluid, rho=1.2, u=700.0, v=30.0, p=101325.0)
+    sim = Euler2D(config=em_config(nx=14, ny=10, initial_condition=ic, fluid=fluid, t_final=0.002), mesh_config=mesh())
+    sim.apply_initial_condition()
+    blk = next(iter(sim.blocks))
+    assert blk.state._uniform is not None            # nothing materialised, nothing uploaded yet
+    uploads = []
+    orig = sim._engine.upload
+    sim._engine.upload = lambda gid, arr: (uploads.append(gid), orig(gid, arr))[1]
+    sim.apply_boundary_condition()
+    assert uploads == []
+    W = np.array([1.2, 700.0, 30.0, 101325.0]).reshape(1, 1, 4)
+    U = cases.prim_to_cons_nd(W)[0, 0]
+    for b in sim.blocks:
+        got = sim._engine.download(b.global_block_num)
+        assert got.shape == (10, 14, 4) and np.all(got == got[0, 0]) and np.array_equal(got[0, 0], U)
+        assert np.array_equal(b.state.data, got)      # host view materialises to the same numbers
+    sim.solve()
+    prob = cases.build_oracle(mesh().dict, 14, 10, lambda x, y: np.broadcast_to(U, x.shape + (4,)).copy())
+    t, dts = prob.run(0.0, 0.002 * 343.0)
+    assert sim.num_time_step == len(dts) and len(dts) >= 2
+    for b in sim.blocks:
+        assert np.array_equal(b.state.data, prob.blocks[b.global_block_num].U)

@@ -2,6 +2,7 @@
 (/root/reference) in the build container (see oracle/refharness.py for the stubs).
 
     python oracle/make_golden.py            # rewrites tests/golden/*.npz
+    python oracle/make_golden.py NAME ...   # only the named fixtures
 
 Each fixture stores the block dictionary (vertices, neighbours, BC types, Dirichlet inlet
 strips), a starting state U0 per block (the reference's own state after `pre` steps, i.e. a
@@ -47,8 +48,14 @@ def ref_blocks(blocks):
     return out
 
 
+ONLY = set()   # fixture names given on the command line (empty = all)
+
+
 def make(name, blocks, nx, ny, ic, pre, steps, note="", **cfg):
     import cases
+
+    if ONLY and name not in ONLY:
+        return
 
     rh.activate()
     kw = dict(nx=nx, ny=ny, initial_condition=rh.CallableIC(lambda x, y: None))
@@ -113,6 +120,7 @@ def make(name, blocks, nx, ny, ic, pre, steps, note="", **cfg):
 def main():
     import cases
 
+    ONLY.update(sys.argv[1:])
     os.makedirs(GOLDEN, exist_ok=True)
     rh.activate()
     rh.patch_hlle()
@@ -139,6 +147,16 @@ def main():
         make(f"em_nqp{nq}", em, 12, 12, cases.explosion_ic, pre=2, steps=3, fvm_num_quadrature_points=nq)
     make("em_hlle_cons_rk2", em, 12, 12, cases.explosion_ic, pre=3, steps=5, note="patched oracle (2 edits)",
          fvm_flux_function_type="HLLE", time_integrator="RK2")
+    # the remaining shipped examples (BASELINE.json configs[3] = jet; supersonic_step, implosion, shockbox)
+    make("jet_hlll_prim_rk2", cases.jet_mesh(6), 36, 6, cases.jet_ic, pre=12, steps=10,
+         fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive")
+    make("jet_hlle_prim_rk2", cases.jet_mesh(6), 36, 6, cases.jet_ic, pre=12, steps=10, note="patched oracle (2 edits)",
+         fvm_flux_function_type="HLLE", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive")
+    make("step_hlll_prim_rk2", cases.step_mesh(8), 24, 8, cases.step_ic, pre=15, steps=10,
+         fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.3, reconstruction_type="primitive")
+    one = cases.em_mesh(nbx=1, nby=1, east=10.0, north=10.0)
+    make("implosion_roe_cons_rk2", one, 24, 24, cases.implosion_ic, pre=6, steps=8, time_integrator="RK2", CFL=0.4)
+    make("shockbox_roe_cons_rk2", one, 24, 24, cases.shockbox_ic, pre=6, steps=8, time_integrator="RK2", CFL=0.4)
 
 
 if __name__ == "__main__":

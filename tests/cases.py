@@ -94,6 +94,83 @@ def wedge_ic(x, y):
     return prim_to_cons_nd(W)
 
 
+def _nd_inlet(W, n):
+    """PrimitiveDirichletBC state tiled to the ghost strip, non-dimensionalised like
+    pyhype/boundary_conditions/base.py:41 does on construction."""
+    inlet = np.tile(np.asarray(W, dtype=float), (n, 1))
+    return inlet / np.array([RHO_INF, A_INF, A_INF, RHO_INF * A_INF**2])
+
+
+def jet_mesh(ny):
+    """examples/jet/mesh.py: nine blocks stacked south -> north, slip walls on the west side except the
+    Dirichlet inlet of the middle block, outflow elsewhere."""
+    inlet = _nd_inlet([1.0, 0.1, 0.0, 2.0 / GAMMA], ny).reshape(ny, 1, 4)
+    return QuadMeshGenerator(
+        nx_blk=1, ny_blk=9, BCE=["OutletDirichlet"] * 9, BCW=["Slipwall"] * 4 + [inlet] + ["Slipwall"] * 4,
+        BCN=["OutletDirichlet"], BCS=["OutletDirichlet"], NE=(1, 0.5), SW=(0, 0), NW=(0, 0.5), SE=(1, 0),
+    ).dict
+
+
+def jet_ic(x, y):
+    """examples/jet/initial_condition.py:33-46 (air at rest, p = 1/gamma), broadcast to the block."""
+    W = np.empty(x.shape + (4,))
+    W[...] = np.array([1.0, 0.0, 0.0, 1 / GAMMA])
+    return prim_to_cons_nd(W)
+
+
+def step_mesh(ny):
+    """examples/supersonic_step/mesh.py (step_ten_block): ten 3 x 1 blocks around a forward-facing step,
+    Mach 5 Dirichlet inlet on the west side, block numbering NOT a regular grid."""
+    inlet = _nd_inlet([1.0, 5.0, 0.0, 1 / 1.4], ny).reshape(ny, 1, 4)
+    wall, out = "Slipwall", "OutletDirichlet"
+    #      gid: (x0, y0,   E     W     N     S,    bcE   bcW    bcN   bcS)
+    spec = {
+        0: (0, 0, None, None, 1, None, wall, inlet, None, wall),
+        1: (0, 1, 6, None, 2, 0, None, inlet, None, None),
+        2: (0, 2, 5, None, 3, 1, None, inlet, None, None),
+        3: (0, 3, 4, None, None, 2, None, inlet, wall, None),
+        4: (3, 3, 9, 3, None, 5, None, None, wall, None),
+        5: (3, 2, 8, 2, 4, 6, None, None, None, None),
+        6: (3, 1, 7, 1, 5, None, None, None, None, wall),
+        7: (6, 1, None, 6, 8, None, out, None, None, wall),
+        8: (6, 2, None, 5, 9, 7, out, None, None, None),
+        9: (6, 3, None, 4, None, 8, out, None, wall, None),
+    }
+    blocks = {}
+    for gid, (x0, y0, nE, nW, nN, nS, bE, bW, bN, bS) in spec.items():
+        blocks[gid] = dict(
+            nBLK=gid, NW=[x0, y0 + 1], NE=[x0 + 3, y0 + 1], SW=[x0, y0], SE=[x0 + 3, y0],
+            NeighborE=nE, NeighborW=nW, NeighborN=nN, NeighborS=nS,
+            NeighborNE=None, NeighborNW=None, NeighborSE=None, NeighborSW=None,
+            BCTypeE=bE, BCTypeW=bW, BCTypeN=bN, BCTypeS=bS,
+            BCTypeNE=None, BCTypeNW=None, BCTypeSE=None, BCTypeSW=None,
+        )
+    return blocks
+
+
+def step_ic(x, y):
+    """pyhype/initial_conditions/supersonic_flood.py with the values of examples/supersonic_step/config.py:8-14."""
+    W = np.empty(x.shape + (4,))
+    W[...] = np.array([1.0, 5.0, 0.0, 1 / GAMMA])
+    return prim_to_cons_nd(W)
+
+
+def _two_state(cond):
+    UL = prim_to_cons_nd(np.array([4.6968, 0.0, 0.0, 404400.0]).reshape(1, 1, 4))
+    UR = prim_to_cons_nd(np.array([1.1742, 0.0, 0.0, 101100.0]).reshape(1, 1, 4))
+    return np.where(cond[..., None], UR, UL)
+
+
+def implosion_ic(x, y):
+    """examples/implosion/initial_condition.py:33-60 (low-pressure corner x, y <= 5)."""
+    return _two_state(np.logical_and(x <= 5, y <= 5))
+
+
+def shockbox_ic(x, y):
+    """examples/shockbox/initial_condition.py:33-63 (two opposite low-pressure quadrants)."""
+    return _two_state(np.logical_or(np.logical_and(x <= 5, y <= 5), np.logical_and(x > 5, y > 5)))
+
+
 def build_oracle(blocks, nx, ny, ic, **kw):
     from oracle import muscl_oracle as mo
 

@@ -400,7 +400,15 @@ int pyh_add_block(void* ctx, const pyh_block_desc* b) {
             D.dir_cons[s] = cons;
         }
     }
-    D.cart = b->is_cartesian;
+    D.cart = b->is_cartesian ? 1 : 0;
+    {   // bit 1: every vertical face of the block has theta == 0 exactly (cos == 1, sin == 0), e.g. the rectangular blocks of
+        // RectagularMeshGenerator, whose corner coordinates fail the reference's exact is_cartesian test;
+        // the rotation into / out of such a face frame is the identity by value (PYH_SKIP_UNIT_ROT, pyh_stage_march.cuh)
+        bool unit = true;
+        const size_t nv = (size_t)ny * (nx + 1);
+        for (size_t i = 0; i < nv && unit; ++i) unit = (b->cos_v[i] == 1.0) && (b->sin_v[i] == 0.0);
+        if (unit) D.cart |= 2;
+    }
     D.gid = b->gid;
     hb.d.nodes_x = hb.d.nodes_y = hb.d.area = hb.d.cos_v = hb.d.sin_v = hb.d.cos_h = hb.d.sin_h = nullptr;
     for (int s = 0; s < 4; ++s) hb.d.dirichlet_prim[s] = nullptr;

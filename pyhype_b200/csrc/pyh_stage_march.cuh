@@ -36,6 +36,9 @@ namespace pyh {
 #ifndef PYH_PAIR_BARRIER
 #define PYH_PAIR_BARRIER 0
 #endif
+#ifndef PYH_SKIP_UNIT_ROT
+#define PYH_SKIP_UNIT_ROT 0
+#endif
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
@@ -85,7 +88,10 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     const BlkDev& B = blks[bz];
     double* __restrict__ const base = B.base;
     const int bcE = B.bc[PYH_EAST], bcW = B.bc[PYH_WEST], bcN = B.bc[PYH_NORTH], bcS = B.bc[PYH_SOUTH];
-    const int cart = B.cart;
+    const int cart = B.cart & 1;
+    // rotation by theta == 0 (u*1 + v*0, v*1 - u*0) returns its argument by value for every finite state: skip it on
+    // blocks whose vertical faces are all axis-aligned (BlkDev::cart bit 1), like the reference does for is_cartesian blocks
+    const bool vident = cart || (PYH_SKIP_UNIT_ROT && (B.cart & 2));
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
     const int j = (int)bx * (NT - 4) - 2 + t;
@@ -164,6 +170,10 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 const unsigned oE = o + 1, oN = o + pitch;
                 // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155)
                 double LE = G[po.Lv + oE], LW = G[po.Lv + o], LN = G[po.Lh + oN], LS = G[po.Lh + o];
+#if PYH_FOLD_POW2
+                // half face weights: (0.5 (q + qE)) * xlE == (q + qE) * (0.5 xlE), both scalings exact (pyh_math.cuh)
+                LE = 0.5 * LE; LW = 0.5 * LW; LN = 0.5 * LN; LS = 0.5 * LS;
+#endif
                 double xlE = LE * G[po.cv + oE], xlW = LW * (-G[po.cv + o]);
                 double xlN = LN * G[po.ch + oN], xlS = LS * (-G[po.ch + o]);
                 double ylE = LE * G[po.sv + oE], ylW = LW * (-G[po.sv + o]);
@@ -188,7 +198,11 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
                     // face averages (quad_block.py:181-218)
+#if PYH_FOLD_POW2
+                    double fE = q + qE, fW = qW + q, fN = q + qN, fS = qS + q;
+#else
                     double fE = 0.5 * (q + qE), fW = 0.5 * (qW + q), fN = 0.5 * (q + qN), fS = 0.5 * (qS + q);
+#endif
                     double gx = (fE * xlE + fW * xlW + fN * xlN + fS * xlS) * ia;
                     double gy = (fE * ylE + fW * ylW + fN * ylN + fS * ylS) * ia;
 #pragma unroll
@@ -267,6 +281,9 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         double IW[4] = {0.0, 0.0, 0.0, 0.0};
         if (full && doV) {
             const double cf = G[po.cv + o], sf = G[po.sv + o], Lf = G[po.Lv + o];
+            // riemann_flux returns flux_scale(FLUX) * F (pyh_math.cuh); the face length absorbs the factor, exactly
+            const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;     // one point:  L * (0 + 2 F)
+            const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;     // 2, 3 points: L * sum_p w_p F_p
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
             for (int p = 0; p < NQ; ++p) {   // one Riemann problem per quadrature point (fvm/base.py:344-351)
@@ -293,7 +310,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     for (int k = 0; k < 4; ++k) QR0[k] = sFE[iFE(par, p, k, t - 1)];         // east-face state of cell (r, nx-1)
                     apply_bc_edge(bcE, PYH_EAST, r, cf, sf, QR0);
                 }
-                if (!cart) { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }      // fvm/base.py:366-376
+                if (!vident) { rot(QL0[1], QL0[2], cf, sf); rot(QR0[1], QR0[2], cf, sf); }    // fvm/base.py:366-376
                 double Fq[4];
                 auto faceV = [&](auto tag) -> bool {
                     constexpr bool FAST = decltype(tag)::value;
@@ -306,14 +323,14 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     } else
 #endif
                     riemann_flux<FLUX, PRIM, FAST>(QL, QR, Fq, C, ok);
-                    if (!cart) unrot(Fq[1], Fq[2], cf, sf);                                  // fvm/base.py:388-390
+                    if (!vident) unrot(Fq[1], Fq[2], cf, sf);                                // fvm/base.py:388-390
                     return ok;
                 };
                 if (!faceV(FastTag{})) faceV(SafeTag{});
                 // integrate_flux (fvm/base.py:188-190): L * (((0 + w0 F0) + w1 F1) + w2 F2); one point: w0 = 2
                 if (NQ == 1) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) IW[k] = Lf * (2.0 * Fq[k]);
+                    for (int k = 0; k < 4; ++k) IW[k] = PYH_FOLD_POW2 ? Lf1 * Fq[k] : Lf * (2.0 * Fq[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[k] = acc[k] + C.qw[p] * Fq[k];
@@ -321,7 +338,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             }
             if (NQ > 1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) IW[k] = Lf * acc[k];
+                for (int k = 0; k < 4; ++k) IW[k] = Lfq * acc[k];
             }
         }
 #pragma unroll
@@ -330,6 +347,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
             const double cf = G[po.ch + o], sf = G[po.sh + o], Lf = G[po.Lh + o];
+            const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;
+            const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;
             double IS[4];
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
@@ -377,7 +396,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 if (!faceH(FastTag{})) faceH(SafeTag{});
                 if (NQ == 1) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) IS[k] = Lf * (2.0 * Fq[k]);
+                    for (int k = 0; k < 4; ++k) IS[k] = PYH_FOLD_POW2 ? Lf1 * Fq[k] : Lf * (2.0 * Fq[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[k] = acc[k] + C.qw[p] * Fq[k];
@@ -385,7 +404,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             }
             if (NQ > 1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) IS[k] = Lf * acc[k];
+                for (int k = 0; k < 4; ++k) IS[k] = Lfq * acc[k];
             }
 
             // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
@@ -401,14 +420,19 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     for (int k = 0; k < 4; ++k) {
                         double IWp = sIW[((par ^ 1) * 4 + k) * NT + t], IEp = sIW[((par ^ 1) * 4 + k) * NT + t + 1];
                         double ISp = sIS[k * NT + t];
+#if PYH_FOLD_POW2
+                        Rk[k] = Ar<FAST>::div(IWp - IEp + ISp - IS[k], ra, ok);        // = 2 R; the 0.5 moves into the RK coefficient
+#else
                         Rk[k] = Ar<FAST>::div(0.5 * (IWp - IEp + ISp - IS[k]), ra, ok);
+#endif
                     }
                     return ok;
                 };
                 if (!resid(FastTag{})) resid(SafeTag{});
+                constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
                 if (plan.write_residual) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = Rk[k];
+                    for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = PYH_FOLD_POW2 ? rscale * Rk[k] : Rk[k];
                 }
                 {
                     // all source loads first, then the updates (targets 0 and 1 by static index: no local copies)
@@ -420,17 +444,17 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + om] : 0.0;
                     }
                     if (nt_ > 0) {
-                        const double c0 = ctl->coef[plan.t[0].coef];
+                        const double c0 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[0].coef] : ctl->coef[plan.t[0].coef];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) base[plan.t[0].dst + k * PL + om] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k];
                     }
                     if (nt_ > 1) {
-                        const double c1 = ctl->coef[plan.t[1].coef];
+                        const double c1 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[1].coef] : ctl->coef[plan.t[1].coef];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) base[plan.t[1].dst + k * PL + om] = plan.t[1].add ? s1[k] + c1 * Rk[k] : s1[k];
                     }
                     for (int q = 2; q < nt_; ++q) {   // tableaux with more than two live rows (e.g. DormandPrince5)
-                        const double cq = ctl->coef[plan.t[q].coef];
+                        const double cq = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[q].coef] : ctl->coef[plan.t[q].coef];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             double src = base[plan.t[q].src + k * PL + om];

@@ -360,9 +360,9 @@ def run_ours(args):
                 "peak_issue_per_s": fp64_peak,
                 "cell_stage_per_s_kernel": cells_local / (kern_ms * 1e-3),
                 # FP64 instructions per cell-stage of the headline scheme, counted by ncu (profiles/r01n_summary.md);
-                # the operation list of SURVEY.md section 8A needs 1187
-                "fp64_instr_per_cell_stage": 1226 if (args.flux == "Roe" and args.recon == "conservative") else None,
-                "frac": (1226 * cells_local / (kern_ms * 1e-3) / fp64_peak) if (args.flux == "Roe" and args.recon == "conservative") else None,
+                # ncu (profiles/r01s_*): 1152 with the exact power-of-two scalings folded; the literal operation list of SURVEY.md section 8A needs 1187
+                "fp64_instr_per_cell_stage": 1152 if (args.flux == "Roe" and args.recon == "conservative") else None,
+                "frac": (1152 * cells_local / (kern_ms * 1e-3) / fp64_peak) if (args.flux == "Roe" and args.recon == "conservative") else None,
             },
         },
     }

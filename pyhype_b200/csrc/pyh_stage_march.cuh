@@ -37,7 +37,7 @@ namespace pyh {
 #define PYH_PAIR_BARRIER 0
 #endif
 #ifndef PYH_SKIP_UNIT_ROT
-#define PYH_SKIP_UNIT_ROT 0
+#define PYH_SKIP_UNIT_ROT 1
 #endif
 
 typedef std::integral_constant<bool, true> FastTag;

@@ -2,7 +2,8 @@
 HOST by g++ (tests/host_twin/) and compared with the oracle bit for bit: every Riemann solver in both
 reconstruction modes, the four limiters, the two emulations of OpenBLAS' x87 dnrm2, the branch-free division /
 reciprocal / square-root sequences -- for the plain-operator policy (Ar<false>, the kernel's fallback) and for the
-branch-free fast policy (Ar<true>, the kernel's hot path), in the default build and in the PYH_FOLD_POW2 build.
+branch-free fast policy (Ar<true>, the kernel's hot path), with every scaling executed literally (PYH_FOLD_POW2=0), in the shipped build (folded scalings) and in the
+PYH_LEAN_CHECKS build.
 This is a check of the SOURCE the stage kernel inlines, on the CPU; the kernel itself is checked by the -m gpu
 tests.  (The MUFU seed instructions are replaced by stand-ins of similar accuracy: the refinement sequences
 converge to the correctly rounded result from any such seed, which is exactly what is verified here.)"""
@@ -31,18 +32,19 @@ def _ptr(a, t=dp):
 
 
 class Twin:
-    def __init__(self, fold):
+    def __init__(self, fold, lean=0):
         os.makedirs(OUT, exist_ok=True)
-        lib = os.path.join(OUT, f"libpyh_twin_fold{fold}.so")
+        lib = os.path.join(OUT, f"libpyh_twin_fold{fold}_lean{lean}.so")
         deps = [SRC, os.path.join(SHIM, "cuda_runtime.h"), os.path.join(CSRC, "pyh_math.cuh"), os.path.join(CSRC, "pyh_fastdiv.cuh")]
         if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
             gxx = shutil.which("g++")
             if gxx is None:
                 pytest.skip("g++ not available")
-            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}",
+            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}", f"-DPYH_LEAN_CHECKS={lean}",
                             "-I", SHIM, "-I", CSRC, "-o", lib, SRC], check=True)
         self.lib = C.CDLL(lib)
         self.lib.twin_flux_scale.restype = C.c_double
+        self.fold, self.lean = fold, lean
         assert self.lib.twin_fold_pow2() == fold
 
     def riemann(self, flux, prim, fast, QL, QR):
@@ -86,9 +88,10 @@ class Twin:
         return W, ok.astype(bool)
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["default", "fold_pow2"])
+# (PYH_FOLD_POW2, PYH_LEAN_CHECKS): the literal operation list, the shipped default, the lean-check build
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (1, 1)], ids=["literal", "fold_pow2", "fold_pow2_lean"])
 def twin(request):
-    return Twin(request.param)
+    return Twin(*request.param)
 
 
 def face_states(n, seed):
@@ -227,3 +230,78 @@ def test_cons_to_prim_matches_oracle(twin):
     for fast in (0, 1):
         Wt, ok = twin.cons2prim(fast, U)
         assert ok.all() and np.array_equal(Wt, ref)
+
+
+SCALES = [-1000, -700, -400, -260, -200, -130, -100, -40, 0, 40, 100, 130, 200, 260, 400, 700, 1000]
+
+
+@pytest.mark.parametrize("flux", ["Roe", "HLLE", "HLLL"])
+@pytest.mark.parametrize("prim", [0, 1], ids=["conservative", "primitive"])
+def test_fast_path_is_sound_for_any_magnitude(twin, flux, prim):
+    """`ok` must imply equality with the oracle whatever the magnitude of the operands: densities, pressures,
+    momenta / velocities and whole states scaled by 2^-1000 .. 2^1000 (the range tests may reject as much as they like,
+    but what they let through has to be right)."""
+    WL0, WR0 = face_states(3000, seed=31)
+    accepted = 0
+    for what in ("rho", "p", "vel", "all"):
+        for k in SCALES:
+            WL, WR = WL0.copy(), WR0.copy()
+            f = 2.0**k
+            with np.errstate(all="ignore"):
+                for Wp in (WL, WR):
+                    if what in ("rho", "all"):
+                        Wp[:, 0] *= f
+                    if what in ("p", "all"):
+                        Wp[:, 3] *= f
+                    if what == "vel":
+                        Wp[:, 1:3] *= f
+                if prim:
+                    QL, QR = WL, WR
+                else:
+                    QL, QR = mo.prim_to_cons(WL, G), mo.prim_to_cons(WR, G)
+                    WL, WR = mo.cons_to_prim(QL, G), mo.cons_to_prim(QR, G)
+                ref = mo.FLUXES[flux](WL, WR, G)
+            F, ok, scale = twin.riemann(FLUX_ID[flux], prim, 1, QL, QR)
+            with np.errstate(all="ignore"):
+                want = scale * ref
+                good = (F == want) | (np.isnan(F) & np.isnan(want))
+                if twin.fold:
+                    # the documented limits of PYH_FOLD_POW2 (pyh_math.cuh): an intermediate in the subnormal range may
+                    # cost one unit of the subnormal grid, and an intermediate that overflows does so one factor of two
+                    # earlier or later -- both far outside any realizable state
+                    good |= (np.abs(F - want) <= 4 * 4.94e-324) | ~np.isfinite(F) | ~np.isfinite(want)
+            bad = np.nonzero(ok & ~np.all(good, axis=1))[0]
+            assert len(bad) == 0, (flux, prim, what, k, len(bad), QL[bad[:1]], QR[bad[:1]], F[bad[:1]], want[bad[:1]])
+            if abs(k) <= 200:   # and inside any physically meaningful range the folded build is exact as well
+                strict = (F == want) | (np.isnan(F) & np.isnan(want))
+                assert np.all(strict[ok]), (flux, prim, what, k)
+            accepted += int(ok.sum())
+    assert accepted > 3000 * 4 * 3      # the moderate scalings are accepted
+
+
+@pytest.mark.parametrize("lim", ["Venkatakrishnan", "VanLeer", "VanAlbada", "BarthJespersen"])
+def test_limiter_fast_path_is_sound_for_any_magnitude(twin, lim):
+    rng = np.random.default_rng(41)
+    n = 4000
+    lid = ["Venkatakrishnan", "VanLeer", "VanAlbada", "BarthJespersen"].index(lim)
+    accepted = 0
+    for kq in SCALES:
+        for kt in (-600, -300, -120, -30, 0, 30, 120, 300, 600):
+            with np.errstate(all="ignore"):
+                q = rng.uniform(-2, 2, n) * 2.0**kq
+                nb = q[:, None] * (1.0 + rng.standard_normal((n, 4)) * rng.choice([1e-12, 1e-6, 1e-2, 1.0], (n, 1)))
+                mx = np.maximum(q, nb.max(axis=1))
+                mn = np.minimum(q, nb.min(axis=1))
+                dmx, dmn = mx - q, mn - q
+                term = rng.standard_normal((n, 4)) * rng.choice([0.0, 1e-9, 1e-3, 0.5], (n, 4)) * np.ldexp(1.0, max(-1070, min(1020, kq + kt)))
+                davg = (q[:, None] + term) - q[:, None]
+                slope = np.where(davg > 0, dmx[:, None] / davg, np.where(davg < 0, dmn[:, None] / davg, 1.0))
+                pf = mo.LIMITERS[lim](slope)
+                ref = np.minimum(np.minimum(np.minimum(pf[:, 0], pf[:, 1]), pf[:, 2]), pf[:, 3])
+            fin = np.isfinite(dmx) & np.isfinite(dmn) & np.all(np.isfinite(davg), axis=1)
+            phi, ok = twin.limiter4(lid, 1, np.ascontiguousarray(dmx), np.ascontiguousarray(dmn), davg)
+            good = (phi == ref) | (np.isnan(phi) & np.isnan(ref))
+            bad = np.nonzero(ok & fin & ~good)[0]
+            assert len(bad) == 0, (lim, kq, kt, len(bad), dmx[bad[:1]], dmn[bad[:1]], davg[bad[:1]], phi[bad[:1]], ref[bad[:1]])
+            accepted += int((ok & fin).sum())
+    assert accepted > n * 20

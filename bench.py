@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--integrator", default="RK4")
     ap.add_argument("--recon", default="conservative", choices=["conservative", "primitive"])
     ap.add_argument("--ic", default="explosion", choices=["explosion", "smooth"], help="diagnostics; the headline workload is 'explosion'")
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=24, help="pipelined end-to-end steps (fill + drain of the three-stream pipeline cost ~2 steps)")
     ap.add_argument("--cpu-block", type=int, default=192, help="block side of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = min(cores, blocks))")

@@ -1,0 +1,184 @@
+// Host twin of the stage kernel: pyhype_b200/csrc/pyh_stage_march.cuh (and the ghost / geometry / layout kernels of
+// pyh_kernels.cuh) compiled by g++ through tests/host_twin/shim and EXECUTED on the CPU -- one OS thread per CUDA
+// thread of a thread block, __syncthreads() as a barrier, thread blocks one after another.  The driver below lays a set
+// of mesh blocks out exactly as pyh_api.cu does (same Layout / PlaneOffsets / BlkDev / StagePlan), refreshes the ghost
+// frame and launches one stage, so tests/test_kernel_twin.py can compare the kernel's residual, gradients, limiter,
+// ghost strips and updated state with the reference fixtures without a GPU.  Test infrastructure only.
+// Build: g++ -O1 -ffp-contract=off -std=c++20 -pthread -shared -fPIC -DPYH_HOST_TWIN -I tests/host_twin/shim
+//        -I pyhype_b200/csrc kernel_twin.cpp
+#define PYH_HOST_TWIN 1
+#include <cuda_runtime.h>   // the shim
+#include <algorithm>
+#include <vector>
+#include "pyh_kernels.cuh"
+#include "pyh_stage_march.cuh"
+
+namespace pyh {
+double smem[(24 + 24 * 3) * 256];   // what `extern __shared__ double smem[]` of the kernel resolves to
+}
+using namespace pyh;
+using pyh_host_twin::launch;
+
+static unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int,
+                        const int, const unsigned long long);
+// Only the instantiations the fixtures use are compiled (each costs ~1 s of g++): every flux x reconstruction mode with
+// the Venkatakrishnan limiter and one quadrature point; the other limiters and 2 / 3 points with Roe + conservative.
+static MarchFn pick(int f, int l, int p, int nq) {
+    if (nq == 1 && l == 0) {
+        switch (2 * f + p) {
+            case 0: return k_stage_march<0, 0, 0, 1>;
+            case 1: return k_stage_march<0, 0, 1, 1>;
+            case 2: return k_stage_march<1, 0, 0, 1>;
+            case 3: return k_stage_march<1, 0, 1, 1>;
+            case 4: return k_stage_march<2, 0, 0, 1>;
+            case 5: return k_stage_march<2, 0, 1, 1>;
+        }
+    }
+    if (f == 0 && p == 0 && nq == 1) {
+        if (l == 1) return k_stage_march<0, 1, 0, 1>;
+        if (l == 2) return k_stage_march<0, 2, 0, 1>;
+        if (l == 3) return k_stage_march<0, 3, 0, 1>;
+    }
+    if (f == 0 && p == 0 && l == 0) {
+        if (nq == 2) return k_stage_march<0, 0, 0, 2>;
+        if (nq == 3) return k_stage_march<0, 0, 0, 3>;
+    }
+    return nullptr;
+}
+
+extern "C" {
+
+int twin_kernel_fold_pow2() { return PYH_FOLD_POW2; }
+
+// One ghost refresh + one stage launch (residual test hook on, one RK target: Unew = U + coef * R) over `nblk` blocks
+// of nx x ny cells.  All arrays are dense, block after block: nodes (ny+1, nx+1); area (ny, nx); cos_v / sin_v
+// (ny, nx+1); cos_h / sin_h (ny+1, nx); nbr / bc (4 per block: E, W, N, S; nbr = local block index or -1);
+// dirichlet: 4 strips per block of (max(nx, ny), 4) primitive inlet states (read only where bc says so);
+// U (ny, nx, 4).  Outputs: R, Unew (ny, nx, 4); G (12, ny, nx) = gx[4], gy[4], phi[4]; ghost (4 sides, max(nx, ny), 4).
+int twin_stage(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int nt, int tys, double gamma, double coef,
+               const double* nodes_x, const double* nodes_y, const double* area, const double* cos_v, const double* sin_v,
+               const double* cos_h, const double* sin_h, const int* nbr, const int* bc, const int* is_cart, const double* dirichlet,
+               const double* U, double* R, double* Unew, double* G, double* ghost) {
+    if (nt < 32 || nt > 256 || nt % 32 || nq < 1 || nq > 3 || tys < 1) return -1;
+    Layout lay;
+    lay.nx = nx; lay.ny = ny;
+    lay.pitch = ((nx + PADL + 1 + 3) / 4) * 4;                     // pyh_create
+    lay.plane = (unsigned)((ny + 2) * lay.pitch);
+    Consts C;
+    C.g = gamma; C.gm1 = gamma - 1.0; C.k = 1.0 / (gamma - 1.0); C.gm = gamma / (gamma - 1.0);
+    for (int q = 0; q < 3; ++q) { C.qw[q] = 0.0; C.qp[q] = 0.0; }
+    if (nq == 1) { C.qp[0] = 0.0; C.qw[0] = 2.0; }
+    else if (nq == 2) { C.qp[0] = -1.0 / std::sqrt(3.0); C.qp[1] = 1.0 / std::sqrt(3.0); C.qw[0] = C.qw[1] = 1.0; }
+    else { C.qp[0] = -std::sqrt(3.0 / 5.0); C.qp[1] = 0.0; C.qp[2] = std::sqrt(3.0 / 5.0); C.qw[0] = 5.0 / 9.0; C.qw[1] = 8.0 / 9.0; C.qw[2] = 5.0 / 9.0; }
+    PlaneOffsets po;
+    std::memset(&po, 0, sizeof(po));
+    {   // pyh_create, one-stage tableau: two state buffers, no accumulator
+        unsigned n = 0;
+        const unsigned PLn = lay.plane;
+        po.H[0] = n * PLn; n += 4;
+        po.H[1] = n * PLn; n += 4;
+        po.A = n++ * PLn;
+        po.dxy = n * PLn; n += 8 * nq;
+        po.Lv = n++ * PLn; po.cv = n++ * PLn; po.sv = n++ * PLn;
+        po.Lh = n++ * PLn; po.ch = n++ * PLn; po.sh = n++ * PLn;
+        po.cdx = n++ * PLn; po.cdy = n++ * PLn;
+        po.nplanes = n;
+    }
+    const size_t nn = (size_t)(ny + 1) * (nx + 1), nc = (size_t)ny * nx, nv = (size_t)ny * (nx + 1), nh = (size_t)(ny + 1) * nx;
+    const int mlen = std::max(nx, ny);
+    std::vector<std::vector<double>> slabs(nblk), dbg(nblk), dbgG(nblk), dirr(nblk * 4), dirc(nblk * 4);
+    std::vector<BlkDev> blks(nblk);
+    Control ctl;
+    std::memset(&ctl, 0, sizeof(ctl));
+    ctl.active = 1;
+    ctl.coef[0] = coef;
+    for (int b = 0; b < nblk; ++b) {
+        slabs[b].assign((size_t)po.nplanes * lay.plane, 0.0);
+        dbg[b].assign(4 * (size_t)lay.plane, 0.0);
+        dbgG[b].assign(12 * (size_t)lay.plane, 0.0);
+        double* slab = slabs[b].data();
+        auto put = [&](const double* host, double* plane, int rows, int cols) {
+            const long long n = (long long)rows * cols;
+            launch(dim3(cdivu(n, 256)), 256, false, [&] { k_dense_to_plane(lay, host, plane, rows, cols); });
+        };
+        put(area + b * nc, slab + po.A, ny, nx);
+        put(cos_v + b * nv, slab + po.cv, ny, nx + 1);
+        put(sin_v + b * nv, slab + po.sv, ny, nx + 1);
+        put(cos_h + b * nh, slab + po.ch, ny + 1, nx);
+        put(sin_h + b * nh, slab + po.sh, ny + 1, nx);
+        launch(dim3(cdivu((long long)nn, 256)), 256, false, [&] {
+            k_geometry(lay, nodes_x + b * nn, nodes_y + b * nn, slab + po.dxy, slab + po.Lv, slab + po.Lh, slab + po.cdx, slab + po.cdy, nq, C);
+        });
+        BlkDev& D = blks[b];
+        std::memset(&D, 0, sizeof(D));
+        D.base = slab;
+        D.dbg = dbg[b].data();
+        D.dbgG = dbgG[b].data();
+        for (int s = 0; s < 4; ++s) {
+            D.bc[s] = bc[4 * b + s];
+            D.nbr[s] = nbr[4 * b + s];
+            D.remote_slot[s] = -1;
+            if (D.bc[s] == PYH_BC_PRIMITIVE_DIRICHLET) {
+                const int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
+                const double* pr = dirichlet + ((size_t)(4 * b + s) * mlen) * 4;
+                dirr[4 * b + s].assign(4 * (size_t)len, 0.0);
+                dirc[4 * b + s].assign(4 * (size_t)len, 0.0);
+                double *rr = dirr[4 * b + s].data(), *cc = dirc[4 * b + s].data();
+                launch(dim3(cdivu(len, 128)), 128, false, [&] { k_dirichlet(pr, rr, cc, len, prim, C); });
+                D.dir_recon[s] = rr;
+                D.dir_cons[s] = cc;
+            }
+        }
+        D.cart = is_cart[b] ? 1 : 0;
+        {   // pyh_add_block: bit 1 = every vertical face axis-aligned
+            bool unit = true;
+            for (size_t i = 0; i < nv && unit; ++i) unit = (cos_v[b * nv + i] == 1.0) && (sin_v[b * nv + i] == 0.0);
+            if (unit) D.cart |= 2;
+        }
+        D.gid = b;
+        launch(dim3(cdivu((long long)nc, 256)), 256, false, [&] { k_aos_to_soa(lay, U + b * nc * 4, slab + po.H[0]); });
+    }
+    // ghost strips + boundary conditions, then the stage
+    launch(dim3(cdivu(mlen, 128), 4, nblk), 128, false, [&] { k_ghost(blks.data(), lay, po, po.H[0], &ctl); });
+    StagePlan plan;
+    std::memset(&plan, 0, sizeof(plan));
+    plan.cur = po.H[0];
+    plan.write_residual = 1;
+    plan.ntargets = 1;
+    plan.t[0].src = po.H[0];
+    plan.t[0].dst = po.H[1];
+    plan.t[0].add = 1;
+    plan.t[0].coef = 0;
+    MarchFn fn = pick(flux, lim, prim, nq);
+    if (!fn) return -2;   // instantiation not compiled into the twin
+    launch(dim3(cdivu(nx, nt - 4), cdivu(ny, tys), nblk), nt, true, [&] { fn(blks.data(), lay, po, plan, &ctl, C, tys, 1, 0, 0ull); });
+    for (int b = 0; b < nblk; ++b) {
+        const double* slab = slabs[b].data();
+        for (int i = 0; i < ny; ++i)
+            for (int j = 0; j < nx; ++j) {
+                const unsigned o = lay.at(i, j);
+                const size_t c = ((size_t)b * nc + (size_t)i * nx + j) * 4;
+                for (int k = 0; k < 4; ++k) {
+                    R[c + k] = dbg[b][k * (size_t)lay.plane + o];
+                    Unew[c + k] = slab[po.H[1] + k * (size_t)lay.plane + o];
+                }
+                for (int k = 0; k < 12; ++k) G[((size_t)b * 12 + k) * nc + (size_t)i * nx + j] = dbgG[b][k * (size_t)lay.plane + o];
+            }
+        for (int s = 0; s < 4; ++s) {
+            const int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
+            for (int idx = 0; idx < len; ++idx) {
+                int gi, gj;
+                if (s == PYH_EAST) { gi = idx; gj = nx; }
+                else if (s == PYH_WEST) { gi = idx; gj = -1; }
+                else if (s == PYH_NORTH) { gi = ny; gj = idx; }
+                else { gi = -1; gj = idx; }
+                for (int k = 0; k < 4; ++k) ghost[(((size_t)b * 4 + s) * mlen + idx) * 4 + k] = slab[po.H[0] + k * (size_t)lay.plane + lay.at(gi, gj)];
+            }
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -3,10 +3,18 @@
 // stage kernel executes can be compared with the oracle on the CPU (tests/test_host_twin.py).  Test
 // infrastructure: nothing under pyhype_b200/ includes or links it.
 #pragma once
+// every standard header first: the CUDA spellings defined below (__noinline__ ...) also occur inside libstdc++
+#include <algorithm>
+#include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
+#include <type_traits>
+#include <vector>
 
 #define __device__
 #define __host__
@@ -32,8 +40,13 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
 static inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll((unsigned long long)x); }
-static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+// CUDA's global min / max overloads (the ones the kernels use; an unsigned-only `max` would silently mangle max(j, -1))
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
 
 // Stand-ins for the MUFU.RCP64H / MUFU.RSQ64H seeds: they see only the high word of the operand and
 // return a high word (low word zero).  The tables of the hardware unit are not reproduced -- any seed
@@ -43,3 +56,56 @@ namespace pyh_host_twin {
 static inline int rcp64h(int hi) { return __double2hiint(1.0 / __hiloint2double(hi, 0)); }
 static inline int rsq64h(int hi) { return __double2hiint(1.0 / std::sqrt(__hiloint2double(hi, 0))); }
 }  // namespace pyh_host_twin
+
+// ---- CTA emulation for tests/host_twin/kernel_twin.cpp: the stage kernel itself runs on the host, one OS thread per
+// CUDA thread of a thread block, __syncthreads() == a std::barrier over the block; thread blocks run one after another.
+#define __launch_bounds__(...)
+#define __shared__
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+inline thread_local dim3 threadIdx;
+inline dim3 blockIdx, blockDim, gridDim;
+
+namespace pyh_host_twin {
+inline std::barrier<>* cta_barrier = nullptr;
+
+// run `body()` for every thread of every block of the grid; with_barrier spawns real threads (needed as soon as the
+// kernel calls __syncthreads), otherwise the threads of a block run one after another on the calling thread
+inline void launch(dim3 grid, unsigned nthreads, bool with_barrier, const std::function<void()>& body) {
+    gridDim = grid;
+    blockDim = dim3(nthreads);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx = dim3(bx, by, bz);
+                if (!with_barrier) {
+                    for (unsigned t = 0; t < nthreads; ++t) { threadIdx = dim3(t); body(); }
+                    continue;
+                }
+                std::barrier<> bar((std::ptrdiff_t)nthreads);
+                cta_barrier = &bar;
+                std::vector<std::thread> th;
+                th.reserve(nthreads);
+                for (unsigned t = 0; t < nthreads; ++t)
+                    th.emplace_back([t, &body, &bar] {
+                        threadIdx = dim3(t);
+                        body();
+                        bar.arrive_and_drop();   // a thread that returns early must not hold the others
+                    });
+                for (auto& x : th) x.join();
+                cta_barrier = nullptr;
+            }
+}
+}  // namespace pyh_host_twin
+
+static inline void __syncthreads() { pyh_host_twin::cta_barrier->arrive_and_wait(); }
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}
+static inline double __longlong_as_double(long long b) { double x; std::memcpy(&x, &b, 8); return x; }
+// k_dt (warp shuffles) is compiled but never run by the twin
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { std::abort(); return v; }
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
+static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }

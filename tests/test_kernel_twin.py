@@ -1,0 +1,124 @@
+"""-m "not gpu": the fused stage kernel itself (pyhype_b200/csrc/pyh_stage_march.cuh, plus the ghost / geometry /
+layout kernels) compiled by g++ and EXECUTED on the CPU by a small thread-block emulator (tests/host_twin/), and
+compared with the golden fixtures of the unmodified reference: ghost strips, Green-Gauss gradients, limiter, residual
+and the state after one Euler update -- by value, max-abs-diff 0, for every fixture (all fluxes, limiters,
+reconstruction modes, 1-3 quadrature points, Dirichlet / slip-wall / outflow edges, irregular block topology) and for
+several thread-block shapes (strip boundaries inside a block, multiple row strips).  This checks the SOURCE of the
+kernel -- indexing, ring buffers, barriers placement, edge handling, arithmetic -- before any GPU time is spent; what
+nvcc makes of it on the device is the business of the -m gpu tests."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_io
+from pyhype_b200.mesh.quad_mesh import QuadMesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host_twin", "kernel_twin.cpp")
+SHIM = os.path.join(ROOT, "tests", "host_twin", "shim")
+CSRC = os.path.join(ROOT, "pyhype_b200", "csrc")
+OUT = os.path.join(ROOT, "build", "host_twin")
+SIDES = ("E", "W", "N", "S")
+FLUX = {"Roe": 0, "HLLE": 1, "HLLL": 2}
+LIM = {"Venkatakrishnan": 0, "VanLeer": 1, "VanAlbada": 2, "BarthJespersen": 3}
+BC = {None: 0, "Reflection": 1, "Slipwall": 2, "OutletDirichlet": 3}
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+# extra -D flags of the builds that are checked: the shipped default and the opt-in variants waiting for GPU time
+BUILDS = {"default": [], "lean_checks": ["-DPYH_LEAN_CHECKS=1"], "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0"]}
+
+
+@pytest.fixture(scope="module", params=list(BUILDS))
+def lib(request):
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, f"libpyh_kernel_twin_{request.param}.so")
+    deps = [SRC, os.path.join(SHIM, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        gxx = shutil.which("g++")
+        if gxx is None:
+            pytest.skip("g++ not available")
+        subprocess.run([gxx, "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-shared", "-fPIC", *BUILDS[request.param], "-I", SHIM,
+                        "-I", CSRC, "-o", so, SRC], check=True)
+    return C.CDLL(so)
+
+
+def run_stage(lib, fx, nt, tys, coef):
+    nx, ny, gids = fx.nx, fx.ny, fx.gids
+    idx = {g: i for i, g in enumerate(gids)}
+    sch = fx.scheme()
+    mlen = max(nx, ny)
+    nb = len(gids)
+    arr = {k: [] for k in ("nodes_x", "nodes_y", "area", "cos_v", "sin_v", "cos_h", "sin_h")}
+    nbr = np.full((nb, 4), -1, dtype=np.int32)
+    bc = np.zeros((nb, 4), dtype=np.int32)
+    cart = np.zeros(nb, dtype=np.int32)
+    dirichlet = np.zeros((nb, 4, mlen, 4))
+    U = np.empty((nb, ny, nx, 4))
+    for g in gids:
+        b = fx.blocks[g]
+        m = QuadMesh(nx, ny, NE=b["NE"], NW=b["NW"], SE=b["SE"], SW=b["SW"])
+        for k in arr:
+            arr[k].append(np.ascontiguousarray(getattr(m, k), dtype=np.float64))
+        cart[idx[g]] = int(m.is_cartesian)
+        for s, side in enumerate(SIDES):
+            n = b["Neighbor" + side]
+            nbr[idx[g], s] = -1 if n is None else idx[n]
+            v = b["BCType" + side]
+            if isinstance(v, np.ndarray):
+                bc[idx[g], s] = 4
+                strip = np.asarray(v, dtype=np.float64).reshape(-1, 4)
+                dirichlet[idx[g], s, : len(strip)] = strip
+            else:
+                bc[idx[g], s] = BC[v]
+        U[idx[g]] = fx[f"U0_{g}"]
+    A = {k: np.ascontiguousarray(np.stack(v)) for k, v in arr.items()}
+    R = np.empty((nb, ny, nx, 4))
+    Un = np.empty((nb, ny, nx, 4))
+    G = np.empty((nb, 12, ny, nx))
+    gh = np.zeros((nb, 4, mlen, 4))
+    p = lambda a, t=dp: a.ctypes.data_as(t)
+    rc = lib.twin_stage(FLUX[sch["flux"]], LIM[sch["limiter"]], int(sch["recon"] == "primitive"), int(sch["nqp"]), nx, ny, nb, nt, tys,
+                        C.c_double(fx.meta["gamma"]), C.c_double(coef), p(A["nodes_x"]), p(A["nodes_y"]), p(A["area"]), p(A["cos_v"]),
+                        p(A["sin_v"]), p(A["cos_h"]), p(A["sin_h"]), p(nbr, ip), p(bc, ip), p(cart, ip), p(dirichlet), p(U), p(R), p(Un),
+                        p(G), p(gh))
+    assert rc == 0
+    return idx, U, R, Un, G, gh
+
+
+def check(fx, idx, U, R, Un, G, gh, coef):
+    nx, ny = fx.nx, fx.ny
+    for g in fx.gids:
+        i = idx[g]
+        for s, side in enumerate(SIDES):
+            ref = fx[f"ghost0_{g}_{side}"].reshape(-1, 4)
+            assert np.array_equal(gh[i, s, : len(ref)], ref), (fx.name, g, side)
+        for k, name in enumerate(("gx", "gy", "phi")):
+            got = np.moveaxis(G[i, 4 * k: 4 * k + 4], 0, -1)
+            assert np.array_equal(got, fx[f"{name}_{g}"]), (fx.name, g, name, np.abs(got - fx[f"{name}_{g}"]).max())
+        assert np.array_equal(R[i], fx[f"R_{g}"]), (fx.name, g, np.abs(R[i] - fx[f"R_{g}"]).max())
+        assert np.array_equal(Un[i], U[i] + coef * fx[f"R_{g}"]), (fx.name, g)      # explicit_runge_kutta.py:84-89
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_stage_kernel_source_matches_reference_fixture(lib, name):
+    fx = golden_io.Fixture(name)
+    coef = 0.37 * float(fx["dts"][0])
+    out = run_stage(lib, fx, nt=128, tys=64, coef=coef)
+    check(fx, *out, coef)
+
+
+@pytest.mark.parametrize("nt,tys", [(32, 5), (64, 4), (96, 7)])
+@pytest.mark.parametrize("name", ["em_ragged_roe_rk4", "dmr_hlll_venkat_prim_rk2", "wedge_roe_cons_rk2", "jet_hlle_prim_rk2",
+                                  "step_hlll_prim_rk2", "em_nqp3", "cart_roe_cons_rk4"])
+def test_stage_kernel_source_with_strip_boundaries_inside_the_block(lib, name, nt, tys):
+    """28- / 60- / 92-column strips and 4- to 7-row strips: block-interior strip seams, ring lanes on real cells, ragged tails."""
+    fx = golden_io.Fixture(name)
+    coef = 0.37 * float(fx["dts"][0])
+    out = run_stage(lib, fx, nt=nt, tys=tys, coef=coef)
+    check(fx, *out, coef)

@@ -2,7 +2,7 @@
 // shim in tests/host_twin/shim (see there).  extern "C" entry points evaluate the SAME source the stage kernel
 // inlines -- the plain-operator policy Ar<false> and the branch-free fast policy Ar<true> -- on arrays, so that
 // tests/test_host_twin.py can compare them with oracle/muscl_oracle.py bit for bit without a GPU.
-// Build: g++ -O2 -ffp-contract=off -shared -fPIC -DPYH_HOST_TWIN -I tests/host_twin/shim -I pyhype_b200/csrc twin.cpp
+// Build: g++ -O2 -ffp-contract=off -std=c++20 -pthread -shared -fPIC -I tests/host_twin/shim -I pyhype_b200/csrc twin.cpp
 #define PYH_HOST_TWIN 1
 #include <cuda_runtime.h>   // the shim
 #include "pyh_math.cuh"

@@ -40,7 +40,7 @@ class Twin:
             gxx = shutil.which("g++")
             if gxx is None:
                 pytest.skip("g++ not available")
-            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}", f"-DPYH_LEAN_CHECKS={lean}",
+            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}", f"-DPYH_LEAN_CHECKS={lean}",
                             "-I", SHIM, "-I", CSRC, "-o", lib, SRC], check=True)
         self.lib = C.CDLL(lib)
         self.lib.twin_flux_scale.restype = C.c_double

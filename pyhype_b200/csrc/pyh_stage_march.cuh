@@ -40,6 +40,21 @@ namespace pyh {
 #define PYH_SKIP_UNIT_ROT 1
 #endif
 
+// PYH_COLD_HOOKS (default 0, to be measured): the test hooks of the kernel (gradient / limiter / residual stores for
+// pyh_debug_fetch and pyh_residual) are small enough for the compiler to predicate, so their address arithmetic is issued
+// for every cell even though the predicate is false in production (~85 of 2612 warp instructions per cell, profiles/
+// r01s_summary.md).  With the flag they sit behind a call to an out-of-line function.
+#ifndef PYH_COLD_HOOKS
+#define PYH_COLD_HOOKS 0
+#endif
+#if PYH_COLD_HOOKS
+static __device__ __noinline__ void hook_store2(double* p, size_t i0, double v0, size_t i1, double v1) { p[i0] = v0; p[i1] = v1; }
+static __device__ __noinline__ void hook_store1(double* p, size_t i0, double v0) { p[i0] = v0; }
+static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t stride, double v0, double v1, double v2, double v3) {
+    p[i0] = v0; p[i0 + stride] = v1; p[i0 + 2 * stride] = v2; p[i0 + 3 * stride] = v3;
+}
+#endif
+
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
@@ -212,7 +227,11 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         sQN[iFE(par, p, k, t)] = gx * dx[p][2] + gy * dy[p][2];
                         sQS[iQW(p, k)] = gx * dx[p][3] + gy * dy[p][3];
                     }
+#if PYH_COLD_HOOKS
+                    if (want_grad_dbg) { if (full && outcol) hook_store2(B.dbgG, k * (size_t)PL + o, gx, (4 + k) * (size_t)PL + o, gy); }
+#else
                     if (want_grad_dbg && full && outcol) { B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; }
+#endif
                 }
                 // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side;
                 // phi is the minimum over every quadrature point of every face
@@ -246,7 +265,11 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         sQN[iFE(par, p, k, t)] = q + phi * term[p][2];
                         sQS[iQW(p, k)] = q + phi * term[p][3];
                     }
+#if PYH_COLD_HOOKS
+                    if (want_grad_dbg) { if (full && outcol) hook_store1(B.dbgG, (8 + k) * (size_t)PL + o, phi); }
+#else
                     if (want_grad_dbg && full && outcol) B.dbgG[(8 + k) * (size_t)PL + o] = phi;
+#endif
                 }
             } else {
 #pragma unroll
@@ -430,10 +453,14 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 };
                 if (!resid(FastTag{})) resid(SafeTag{});
                 constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
+#if PYH_COLD_HOOKS
+                if (plan.write_residual) hook_store4(B.dbg, om, (size_t)PL, rscale * Rk[0], rscale * Rk[1], rscale * Rk[2], rscale * Rk[3]);
+#else
                 if (plan.write_residual) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = PYH_FOLD_POW2 ? rscale * Rk[k] : Rk[k];
                 }
+#endif
                 {
                     // all source loads first, then the updates (targets 0 and 1 by static index: no local copies)
                     const int nt_ = plan.ntargets;

@@ -36,6 +36,16 @@ namespace pyh {
 #ifndef PYH_PAIR_BARRIER
 #define PYH_PAIR_BARRIER 0
 #endif
+// unroll factors of the two per-variable loops of phase B (1 = rolled: the register file only holds one variable's working
+// set; 2 and 4 still compile to <= 128 registers without spills and give the scheduler two / four variables' division
+// chains to interleave -- knobs for tools/build_variant.sh, not yet measured)
+#ifndef PYH_UNROLL_B1
+#define PYH_UNROLL_B1 1
+#endif
+#ifndef PYH_UNROLL_B2
+#define PYH_UNROLL_B2 1
+#endif
+constexpr int kUnrollB1 = PYH_UNROLL_B1, kUnrollB2 = PYH_UNROLL_B2;   // (#pragma unroll does not expand macros)
 #ifndef PYH_SKIP_UNIT_ROT
 #define PYH_SKIP_UNIT_ROT 1
 #endif
@@ -208,7 +218,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 if (!okA) ia = 1.0 / Acell;
                 // pass 1: gradient and the high-order terms of the four faces (at every quadrature point); the
                 // terms wait in this thread's own face-state slots so that no geometry is live while the limiter divides
-#pragma unroll 1
+#pragma unroll kUnrollB1
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
@@ -235,7 +245,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 }
                 // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side;
                 // phi is the minimum over every quadrature point of every face
-#pragma unroll 1
+#pragma unroll kUnrollB2
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];

@@ -264,6 +264,11 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 #pragma unroll
                         for (int f = 0; f < 4; ++f) davg[f] = (q + term[p][f]) - q;   // limiters/base.py:99-102
                         double pp;
+#if PYH_UNIFORM_SHORTCUT
+                        // locally constant reconstruction: slope = 1 on every face (limiters/base.py:213-221); see pyh_math.cuh
+                        if (davg[0] == 0.0 && davg[1] == 0.0 && davg[2] == 0.0 && davg[3] == 0.0) pp = limiter_at_one<LIM>();
+                        else
+#endif
                         if (!limiter4_fast<LIM>(dmx, dmn, davg, pp)) limiter4_safe<LIM>(dmx, dmn, davg, pp);
                         phi = (p == 0) ? pp : dmin2(phi, pp);
                     }

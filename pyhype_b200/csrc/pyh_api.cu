@@ -11,6 +11,7 @@
 
 #include "pyh_kernels.cuh"
 #include "pyh_march_tu.cuh"
+#include "pyh_plan.cuh"
 
 using namespace pyh;
 
@@ -194,24 +195,7 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, bool overlapp
 // RK partial-sum plan for stage s (explicit_runge_kutta.py:63-75 restated as running sums:
 // row s' accumulates U0 + sum_{k<=s} (dt*a[s'][k]) R_k in k order, exactly the reference's order)
 StagePlan make_plan(Ctx* c, int s, int cur, int next) {
-    StagePlan p;
-    memset(&p, 0, sizeof(p));
-    p.cur = c->po.H[cur];
-    const int S = c->cfg.num_stages;
-    auto a = [&](int r, int k) { return c->tab.a[r * PYH_MAX_STAGES + k]; };
-    for (int r = s; r < S; ++r) {
-        bool prior = false;
-        for (int k = 0; k < s; ++k) if (a(r, k) != 0.0) prior = true;
-        bool nz = a(r, s) != 0.0;
-        if (r != s && !nz) continue;
-        RkTarget t;
-        t.src = prior ? c->po.P[r] : c->po.H[c->i0];
-        t.dst = (r == s) ? c->po.H[next] : c->po.P[r];
-        t.add = nz ? 1 : 0;
-        t.coef = r * PYH_MAX_STAGES + s;
-        p.t[p.ntargets++] = t;
-    }
-    return p;
+    return plan_stage(c->tab.a, c->cfg.num_stages, c->po, c->i0, s, cur, next);   // pyh_plan.cuh
 }
 
 int do_ghost(Ctx* c, int buf) {
@@ -226,9 +210,7 @@ int do_ghost(Ctx* c, int buf) {
 int do_stage(Ctx* c, int s, bool overlapped = false) {
     const int S = c->cfg.num_stages;
     int cur = (s == 0) ? c->i0 : c->cur;
-    int next;
-    if (s == S - 1) next = (S == 1) ? c->i1 : c->i0;
-    else next = (cur == c->i1) ? c->i2 : c->i1;
+    const int next = plan_next_buffer(S, s, cur, c->i0, c->i1, c->i2);
     StagePlan p = make_plan(c, s, cur, next);
     int rc = launch_stage(c, p, 0, overlapped);
     if (rc) return rc;
@@ -300,26 +282,8 @@ int pyh_create(const pyh_config* cfg, void** out) {
     c->tab.nstages = cfg->num_stages;
     for (int s = 0; s < cfg->num_stages; ++s)
         for (int k = 0; k <= s; ++k) c->tab.a[s * PYH_MAX_STAGES + k] = cfg->tableau[s * PYH_MAX_STAGES + k];
-    for (int r = 0; r < PYH_MAX_STAGES; ++r) {
-        c->need_acc[r] = false;
-        for (int k = 0; k < r && r < cfg->num_stages; ++k)
-            if (c->tab.a[r * PYH_MAX_STAGES + k] != 0.0) c->need_acc[r] = true;
-    }
-    {   // slab layout: plane indices -> element offsets
-        unsigned n = 0;
-        const unsigned PLn = c->lay.plane;
-        PlaneOffsets& po = c->po;
-        memset(&po, 0, sizeof(po));
-        const int nH = cfg->num_stages >= 3 ? 3 : 2;
-        for (int h = 0; h < 3; ++h) { po.H[h] = (h < nH) ? n * PLn : 0; if (h < nH) n += 4; }
-        for (int r = 0; r < cfg->num_stages; ++r) if (c->need_acc[r]) { po.P[r] = n * PLn; n += 4; }
-        po.A = n++ * PLn;
-        po.dxy = n * PLn; n += 8 * cfg->num_quadrature_points;
-        po.Lv = n++ * PLn; po.cv = n++ * PLn; po.sv = n++ * PLn;
-        po.Lh = n++ * PLn; po.ch = n++ * PLn; po.sh = n++ * PLn;
-        po.cdx = n++ * PLn; po.cdy = n++ * PLn;
-        po.nplanes = n;
-    }
+    plan_need_acc(c->tab.a, cfg->num_stages, c->need_acc);                                               // pyh_plan.cuh
+    c->po = plan_offsets(c->lay.plane, cfg->num_stages, cfg->num_quadrature_points, c->need_acc);       // slab layout
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
     Control h;

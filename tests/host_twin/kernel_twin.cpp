@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 #include "pyh_kernels.cuh"
+#include "pyh_plan.cuh"
 #include "pyh_stage_march.cuh"
 
 namespace pyh {
@@ -52,119 +53,139 @@ extern "C" {
 
 int twin_kernel_fold_pow2() { return PYH_FOLD_POW2; }
 
-// One ghost refresh + one stage launch (residual test hook on, one RK target: Unew = U + coef * R) over `nblk` blocks
-// of nx x ny cells.  All arrays are dense, block after block: nodes (ny+1, nx+1); area (ny, nx); cos_v / sin_v
-// (ny, nx+1); cos_h / sin_h (ny+1, nx); nbr / bc (4 per block: E, W, N, S; nbr = local block index or -1);
-// dirichlet: 4 strips per block of (max(nx, ny), 4) primitive inlet states (read only where bc says so);
-// U (ny, nx, 4).  Outputs: R, Unew (ny, nx, 4); G (12, ny, nx) = gx[4], gy[4], phi[4]; ghost (4 sides, max(nx, ny), 4).
+// Everything pyh_create / pyh_add_block / pyh_upload_state set up, on the host: slabs laid out by plan_offsets, geometry
+// planes, Dirichlet strips, BlkDev records, the state in H[0].  All arrays are dense, block after block: nodes
+// (ny+1, nx+1); area (ny, nx); cos_v / sin_v (ny, nx+1); cos_h / sin_h (ny+1, nx); nbr / bc (4 per block: E, W, N, S;
+// nbr = local block index or -1); dirichlet: 4 strips per block of (max(nx, ny), 4) primitive inlet states (read only
+// where bc says so); U (ny, nx, 4).
+struct Twin {
+    Layout lay;
+    Consts C;
+    PlaneOffsets po;
+    Control ctl;
+    int nx, ny, nblk, nq, nt, tys, prim, mlen;
+    size_t nc;
+    std::vector<std::vector<double>> slabs, dbg, dbgG, dirr, dirc;
+    std::vector<BlkDev> blks;
+    MarchFn fn;
+
+    int setup(int flux, int lim, int prim_, int nq_, int nx_, int ny_, int nblk_, int nt_, int tys_, double gamma, int S, const double* tab,
+              const double* nodes_x, const double* nodes_y, const double* area, const double* cos_v, const double* sin_v,
+              const double* cos_h, const double* sin_h, const int* nbr, const int* bc, const int* is_cart, const double* dirichlet,
+              const double* U) {
+        nx = nx_; ny = ny_; nblk = nblk_; nq = nq_; nt = nt_; tys = tys_; prim = prim_;
+        if (nt < 32 || nt > 256 || nt % 32 || nq < 1 || nq > 3 || tys < 1 || S < 1 || S > PYH_MAX_STAGES) return -1;
+        fn = pick(flux, lim, prim, nq);
+        if (!fn) return -2;   // instantiation not compiled into the twin
+        lay.nx = nx; lay.ny = ny;
+        lay.pitch = ((nx + PADL + 1 + 3) / 4) * 4;                     // pyh_create
+        lay.plane = (unsigned)((ny + 2) * lay.pitch);
+        C.g = gamma; C.gm1 = gamma - 1.0; C.k = 1.0 / (gamma - 1.0); C.gm = gamma / (gamma - 1.0);
+        for (int q = 0; q < 3; ++q) { C.qw[q] = 0.0; C.qp[q] = 0.0; }
+        if (nq == 1) { C.qp[0] = 0.0; C.qw[0] = 2.0; }
+        else if (nq == 2) { C.qp[0] = -1.0 / std::sqrt(3.0); C.qp[1] = 1.0 / std::sqrt(3.0); C.qw[0] = C.qw[1] = 1.0; }
+        else { C.qp[0] = -std::sqrt(3.0 / 5.0); C.qp[1] = 0.0; C.qp[2] = std::sqrt(3.0 / 5.0); C.qw[0] = 5.0 / 9.0; C.qw[1] = 8.0 / 9.0; C.qw[2] = 5.0 / 9.0; }
+        bool need_acc[PYH_MAX_STAGES];
+        plan_need_acc(tab, S, need_acc);
+        po = plan_offsets(lay.plane, S, nq, need_acc);                  // the product's slab layout (pyh_plan.cuh)
+        const size_t nn = (size_t)(ny + 1) * (nx + 1), nv = (size_t)ny * (nx + 1), nh = (size_t)(ny + 1) * nx;
+        nc = (size_t)ny * nx;
+        mlen = std::max(nx, ny);
+        slabs.assign(nblk, {}); dbg.assign(nblk, {}); dbgG.assign(nblk, {}); dirr.assign(nblk * 4, {}); dirc.assign(nblk * 4, {});
+        blks.assign(nblk, BlkDev());
+        std::memset(&ctl, 0, sizeof(ctl));
+        ctl.active = 1;
+        for (int b = 0; b < nblk; ++b) {
+            slabs[b].assign((size_t)po.nplanes * lay.plane, 0.0);
+            dbg[b].assign(4 * (size_t)lay.plane, 0.0);
+            dbgG[b].assign(12 * (size_t)lay.plane, 0.0);
+            double* slab = slabs[b].data();
+            auto put = [&](const double* host, double* plane, int rows, int cols) {
+                const long long n = (long long)rows * cols;
+                launch(dim3(cdivu(n, 256)), 256, false, [&] { k_dense_to_plane(lay, host, plane, rows, cols); });
+            };
+            put(area + b * nc, slab + po.A, ny, nx);
+            put(cos_v + b * nv, slab + po.cv, ny, nx + 1);
+            put(sin_v + b * nv, slab + po.sv, ny, nx + 1);
+            put(cos_h + b * nh, slab + po.ch, ny + 1, nx);
+            put(sin_h + b * nh, slab + po.sh, ny + 1, nx);
+            launch(dim3(cdivu((long long)nn, 256)), 256, false, [&] {
+                k_geometry(lay, nodes_x + b * nn, nodes_y + b * nn, slab + po.dxy, slab + po.Lv, slab + po.Lh, slab + po.cdx, slab + po.cdy, nq, C);
+            });
+            BlkDev& D = blks[b];
+            std::memset(&D, 0, sizeof(D));
+            D.base = slab;
+            D.dbg = dbg[b].data();
+            D.dbgG = dbgG[b].data();
+            for (int s = 0; s < 4; ++s) {
+                D.bc[s] = bc[4 * b + s];
+                D.nbr[s] = nbr[4 * b + s];
+                D.remote_slot[s] = -1;
+                if (D.bc[s] == PYH_BC_PRIMITIVE_DIRICHLET) {
+                    const int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
+                    const double* pr = dirichlet + ((size_t)(4 * b + s) * mlen) * 4;
+                    dirr[4 * b + s].assign(4 * (size_t)len, 0.0);
+                    dirc[4 * b + s].assign(4 * (size_t)len, 0.0);
+                    double *rr = dirr[4 * b + s].data(), *cc = dirc[4 * b + s].data();
+                    launch(dim3(cdivu(len, 128)), 128, false, [&] { k_dirichlet(pr, rr, cc, len, prim, C); });
+                    D.dir_recon[s] = rr;
+                    D.dir_cons[s] = cc;
+                }
+            }
+            D.cart = is_cart[b] ? 1 : 0;
+            {   // pyh_add_block: bit 1 = every vertical face axis-aligned
+                bool unit = true;
+                for (size_t i = 0; i < nv && unit; ++i) unit = (cos_v[b * nv + i] == 1.0) && (sin_v[b * nv + i] == 0.0);
+                if (unit) D.cart |= 2;
+            }
+            D.gid = b;
+            launch(dim3(cdivu((long long)nc, 256)), 256, false, [&] { k_aos_to_soa(lay, U + b * nc * 4, slab + po.H[0]); });
+        }
+        return 0;
+    }
+    void ghost(int buf) {   // do_ghost
+        launch(dim3(cdivu(mlen, 128), 4, nblk), 128, false, [&] { k_ghost(blks.data(), lay, po, po.H[buf], &ctl); });
+    }
+    void stage(const StagePlan& plan, int want_grad_dbg) {   // launch_stage
+        launch(dim3(cdivu(nx, nt - 4), cdivu(ny, tys), nblk), nt, true, [&] { fn(blks.data(), lay, po, plan, &ctl, C, tys, want_grad_dbg, 0, 0ull); });
+    }
+    void fetch_state(int buf, double* out) const {
+        for (int b = 0; b < nblk; ++b)
+            for (int i = 0; i < ny; ++i)
+                for (int j = 0; j < nx; ++j)
+                    for (int k = 0; k < 4; ++k)
+                        out[((size_t)b * nc + (size_t)i * nx + j) * 4 + k] = slabs[b][po.H[buf] + k * (size_t)lay.plane + lay.at(i, j)];
+    }
+};
+
+// One ghost refresh + one stage launch (residual test hook on, one RK target: Unew = U + coef * R).
+// Outputs: R, Unew (ny, nx, 4); G (12, ny, nx) = gx[4], gy[4], phi[4]; ghost (4 sides, max(nx, ny), 4).
 int twin_stage(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int nt, int tys, double gamma, double coef,
                const double* nodes_x, const double* nodes_y, const double* area, const double* cos_v, const double* sin_v,
                const double* cos_h, const double* sin_h, const int* nbr, const int* bc, const int* is_cart, const double* dirichlet,
                const double* U, double* R, double* Unew, double* G, double* ghost) {
-    if (nt < 32 || nt > 256 || nt % 32 || nq < 1 || nq > 3 || tys < 1) return -1;
-    Layout lay;
-    lay.nx = nx; lay.ny = ny;
-    lay.pitch = ((nx + PADL + 1 + 3) / 4) * 4;                     // pyh_create
-    lay.plane = (unsigned)((ny + 2) * lay.pitch);
-    Consts C;
-    C.g = gamma; C.gm1 = gamma - 1.0; C.k = 1.0 / (gamma - 1.0); C.gm = gamma / (gamma - 1.0);
-    for (int q = 0; q < 3; ++q) { C.qw[q] = 0.0; C.qp[q] = 0.0; }
-    if (nq == 1) { C.qp[0] = 0.0; C.qw[0] = 2.0; }
-    else if (nq == 2) { C.qp[0] = -1.0 / std::sqrt(3.0); C.qp[1] = 1.0 / std::sqrt(3.0); C.qw[0] = C.qw[1] = 1.0; }
-    else { C.qp[0] = -std::sqrt(3.0 / 5.0); C.qp[1] = 0.0; C.qp[2] = std::sqrt(3.0 / 5.0); C.qw[0] = 5.0 / 9.0; C.qw[1] = 8.0 / 9.0; C.qw[2] = 5.0 / 9.0; }
-    PlaneOffsets po;
-    std::memset(&po, 0, sizeof(po));
-    {   // pyh_create, one-stage tableau: two state buffers, no accumulator
-        unsigned n = 0;
-        const unsigned PLn = lay.plane;
-        po.H[0] = n * PLn; n += 4;
-        po.H[1] = n * PLn; n += 4;
-        po.A = n++ * PLn;
-        po.dxy = n * PLn; n += 8 * nq;
-        po.Lv = n++ * PLn; po.cv = n++ * PLn; po.sv = n++ * PLn;
-        po.Lh = n++ * PLn; po.ch = n++ * PLn; po.sh = n++ * PLn;
-        po.cdx = n++ * PLn; po.cdy = n++ * PLn;
-        po.nplanes = n;
-    }
-    const size_t nn = (size_t)(ny + 1) * (nx + 1), nc = (size_t)ny * nx, nv = (size_t)ny * (nx + 1), nh = (size_t)(ny + 1) * nx;
-    const int mlen = std::max(nx, ny);
-    std::vector<std::vector<double>> slabs(nblk), dbg(nblk), dbgG(nblk), dirr(nblk * 4), dirc(nblk * 4);
-    std::vector<BlkDev> blks(nblk);
-    Control ctl;
-    std::memset(&ctl, 0, sizeof(ctl));
-    ctl.active = 1;
-    ctl.coef[0] = coef;
-    for (int b = 0; b < nblk; ++b) {
-        slabs[b].assign((size_t)po.nplanes * lay.plane, 0.0);
-        dbg[b].assign(4 * (size_t)lay.plane, 0.0);
-        dbgG[b].assign(12 * (size_t)lay.plane, 0.0);
-        double* slab = slabs[b].data();
-        auto put = [&](const double* host, double* plane, int rows, int cols) {
-            const long long n = (long long)rows * cols;
-            launch(dim3(cdivu(n, 256)), 256, false, [&] { k_dense_to_plane(lay, host, plane, rows, cols); });
-        };
-        put(area + b * nc, slab + po.A, ny, nx);
-        put(cos_v + b * nv, slab + po.cv, ny, nx + 1);
-        put(sin_v + b * nv, slab + po.sv, ny, nx + 1);
-        put(cos_h + b * nh, slab + po.ch, ny + 1, nx);
-        put(sin_h + b * nh, slab + po.sh, ny + 1, nx);
-        launch(dim3(cdivu((long long)nn, 256)), 256, false, [&] {
-            k_geometry(lay, nodes_x + b * nn, nodes_y + b * nn, slab + po.dxy, slab + po.Lv, slab + po.Lh, slab + po.cdx, slab + po.cdy, nq, C);
-        });
-        BlkDev& D = blks[b];
-        std::memset(&D, 0, sizeof(D));
-        D.base = slab;
-        D.dbg = dbg[b].data();
-        D.dbgG = dbgG[b].data();
-        for (int s = 0; s < 4; ++s) {
-            D.bc[s] = bc[4 * b + s];
-            D.nbr[s] = nbr[4 * b + s];
-            D.remote_slot[s] = -1;
-            if (D.bc[s] == PYH_BC_PRIMITIVE_DIRICHLET) {
-                const int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
-                const double* pr = dirichlet + ((size_t)(4 * b + s) * mlen) * 4;
-                dirr[4 * b + s].assign(4 * (size_t)len, 0.0);
-                dirc[4 * b + s].assign(4 * (size_t)len, 0.0);
-                double *rr = dirr[4 * b + s].data(), *cc = dirc[4 * b + s].data();
-                launch(dim3(cdivu(len, 128)), 128, false, [&] { k_dirichlet(pr, rr, cc, len, prim, C); });
-                D.dir_recon[s] = rr;
-                D.dir_cons[s] = cc;
-            }
-        }
-        D.cart = is_cart[b] ? 1 : 0;
-        {   // pyh_add_block: bit 1 = every vertical face axis-aligned
-            bool unit = true;
-            for (size_t i = 0; i < nv && unit; ++i) unit = (cos_v[b * nv + i] == 1.0) && (sin_v[b * nv + i] == 0.0);
-            if (unit) D.cart |= 2;
-        }
-        D.gid = b;
-        launch(dim3(cdivu((long long)nc, 256)), 256, false, [&] { k_aos_to_soa(lay, U + b * nc * 4, slab + po.H[0]); });
-    }
-    // ghost strips + boundary conditions, then the stage
-    launch(dim3(cdivu(mlen, 128), 4, nblk), 128, false, [&] { k_ghost(blks.data(), lay, po, po.H[0], &ctl); });
-    StagePlan plan;
-    std::memset(&plan, 0, sizeof(plan));
-    plan.cur = po.H[0];
+    double tab[PYH_MAX_STAGES * PYH_MAX_STAGES] = {1.0};
+    Twin T;
+    int rc = T.setup(flux, lim, prim, nq, nx, ny, nblk, nt, tys, gamma, 1, tab, nodes_x, nodes_y, area, cos_v, sin_v, cos_h, sin_h, nbr, bc,
+                     is_cart, dirichlet, U);
+    if (rc) return rc;
+    T.ctl.coef[0] = coef;
+    T.ghost(0);
+    StagePlan plan = plan_stage(tab, 1, T.po, 0, 0, 0, 1);
     plan.write_residual = 1;
-    plan.ntargets = 1;
-    plan.t[0].src = po.H[0];
-    plan.t[0].dst = po.H[1];
-    plan.t[0].add = 1;
-    plan.t[0].coef = 0;
-    MarchFn fn = pick(flux, lim, prim, nq);
-    if (!fn) return -2;   // instantiation not compiled into the twin
-    launch(dim3(cdivu(nx, nt - 4), cdivu(ny, tys), nblk), nt, true, [&] { fn(blks.data(), lay, po, plan, &ctl, C, tys, 1, 0, 0ull); });
+    T.stage(plan, 1);
+    const Layout& lay = T.lay;
+    const size_t nc = T.nc;
+    const int mlen = T.mlen;
+    T.fetch_state(1, Unew);
     for (int b = 0; b < nblk; ++b) {
-        const double* slab = slabs[b].data();
+        const double* slab = T.slabs[b].data();
         for (int i = 0; i < ny; ++i)
             for (int j = 0; j < nx; ++j) {
                 const unsigned o = lay.at(i, j);
                 const size_t c = ((size_t)b * nc + (size_t)i * nx + j) * 4;
-                for (int k = 0; k < 4; ++k) {
-                    R[c + k] = dbg[b][k * (size_t)lay.plane + o];
-                    Unew[c + k] = slab[po.H[1] + k * (size_t)lay.plane + o];
-                }
-                for (int k = 0; k < 12; ++k) G[((size_t)b * 12 + k) * nc + (size_t)i * nx + j] = dbgG[b][k * (size_t)lay.plane + o];
+                for (int k = 0; k < 4; ++k) R[c + k] = T.dbg[b][k * (size_t)lay.plane + o];
+                for (int k = 0; k < 12; ++k) G[((size_t)b * 12 + k) * nc + (size_t)i * nx + j] = T.dbgG[b][k * (size_t)lay.plane + o];
             }
         for (int s = 0; s < 4; ++s) {
             const int len = (s == PYH_EAST || s == PYH_WEST) ? ny : nx;
@@ -174,10 +195,42 @@ int twin_stage(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, in
                 else if (s == PYH_WEST) { gi = idx; gj = -1; }
                 else if (s == PYH_NORTH) { gi = ny; gj = idx; }
                 else { gi = -1; gj = idx; }
-                for (int k = 0; k < 4; ++k) ghost[(((size_t)b * 4 + s) * mlen + idx) * 4 + k] = slab[po.H[0] + k * (size_t)lay.plane + lay.at(gi, gj)];
+                for (int k = 0; k < 4; ++k) ghost[(((size_t)b * 4 + s) * mlen + idx) * 4 + k] = slab[T.po.H[0] + k * (size_t)lay.plane + lay.at(gi, gj)];
             }
         }
     }
+    return 0;
+}
+
+// `nsteps` whole time steps of an S-stage tableau (row-major PYH_MAX_STAGES x PYH_MAX_STAGES) with given dt's, driven like
+// pyh_step: k_set_dt's coefficient table, then per stage plan_next_buffer / plan_stage (pyh_plan.cuh), the stage kernel
+// and the ghost refresh of the buffer it wrote.  The CFL reduction (warp shuffles) is not emulated: dt comes from the caller.
+int twin_steps(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int nt, int tys, double gamma, int S, const double* tab,
+               int nsteps, const double* dts, const double* nodes_x, const double* nodes_y, const double* area, const double* cos_v,
+               const double* sin_v, const double* cos_h, const double* sin_h, const int* nbr, const int* bc, const int* is_cart,
+               const double* dirichlet, const double* U, double* Uout) {
+    Twin T;
+    int rc = T.setup(flux, lim, prim, nq, nx, ny, nblk, nt, tys, gamma, S, tab, nodes_x, nodes_y, area, cos_v, sin_v, cos_h, sin_h, nbr, bc,
+                     is_cart, dirichlet, U);
+    if (rc) return rc;
+    int i0 = 0, i1 = 1, i2 = 2, cur = 0;      // Ctx::i0, i1, i2, cur
+    T.ghost(i0);                               // pyh_apply_bc after the upload
+    for (int n = 0; n < nsteps; ++n) {
+        for (int s = 0; s < S; ++s)            // k_set_dt (explicit_runge_kutta.py:71: dt * a[s][k] formed first)
+            for (int k = 0; k <= s; ++k) T.ctl.coef[s * PYH_MAX_STAGES + k] = dts[n] * tab[s * PYH_MAX_STAGES + k];
+        for (int s = 0; s < S; ++s) {          // do_stage + do_ghost
+            cur = (s == 0) ? i0 : cur;
+            const int next = plan_next_buffer(S, s, cur, i0, i1, i2);
+            T.stage(plan_stage(tab, S, T.po, i0, s, cur, next), 0);
+            cur = next;
+            if (s == S - 1) {
+                if (S == 1) std::swap(i0, i1);
+                cur = i0;
+            }
+            T.ghost(cur);
+        }
+    }
+    T.fetch_state(i0, Uout);
     return 0;
 }
 

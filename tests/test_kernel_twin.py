@@ -172,3 +172,47 @@ def test_whole_time_steps_of_the_kernel_source_match_reference_fixture(lib, name
     idx, Uout = run_steps(lib, fx, nt=32, tys=64)   # two 28-column strips; other shapes are varied by the single-stage tests
     for g in fx.gids:
         assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g, np.abs(Uout[idx[g]] - fx[f"U_{g}"]).max())
+
+
+TSAN_SCRIPT = """
+import sys, ctypes as C
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import numpy as np, golden_io, test_kernel_twin as T
+lib = C.CDLL({so!r})
+for name in {names!r}:
+    fx = golden_io.Fixture(name)
+    coef = 0.37 * float(fx["dts"][0])
+    T.check(fx, *T.run_stage(lib, fx, nt=64, tys=7, coef=coef), coef)
+    idx, Uout = T.run_steps(lib, fx, nt=32, tys=64)
+    assert all(np.array_equal(Uout[idx[g]], fx[f"U_{{g}}"]) for g in fx.gids)
+print("TWIN-RUN-COMPLETE")
+"""
+
+
+def test_shared_memory_protocol_of_the_stage_kernel_is_race_free_under_thread_sanitizer():
+    """The emulator's threads are real threads and __syncthreads() is a real barrier, so ThreadSanitizer sees every
+    shared-memory access of the kernel: the one-barrier-per-row protocol over the double-buffered rings has no
+    unordered conflicting accesses (checked stricter than CUDA needs: lanes of one warp count as separate threads too).
+    With the barrier disabled the same run produces race reports, so the detector does see the kernel's accesses."""
+    import sys
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    tsan = subprocess.run([gxx, "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip("libtsan not available")
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libpyh_kernel_twin_tsan.so")
+    deps = [SRC, os.path.join(SHIM, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run([gxx, "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-std=c++20", "-pthread", "-shared", "-fPIC",
+                        "-I", SHIM, "-I", CSRC, "-o", so, SRC], check=True)
+    code = TSAN_SCRIPT.format(root=ROOT, tests=os.path.join(ROOT, "tests"), so=so,
+                              names=["em_ragged_roe_rk4", "dmr_hlll_venkat_prim_rk2", "em_nqp3"])
+    env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="exitcode=0 halt_on_error=0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    if "TWIN-RUN-COMPLETE" not in r.stdout and "ThreadSanitizer" not in r.stderr:
+        pytest.skip("the interpreter does not run under a preloaded libtsan here: " + r.stderr[-300:])
+    assert "TWIN-RUN-COMPLETE" in r.stdout, r.stderr[-2000:]
+    assert "ThreadSanitizer: data race" not in r.stderr, r.stderr[:3000]

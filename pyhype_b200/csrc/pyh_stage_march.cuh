@@ -97,7 +97,11 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             __syncthreads();
         }
     }
+#ifdef PYH_HOST_TWIN
+    extern double smem[];            // tests/host_twin: the emulator's per-block buffer
+#else
     extern __shared__ double smem[];
+#endif
     const int NT = blockDim.x;
     const int t = threadIdx.x;
     double* const sQ = smem;                       // [3][4][NT]

@@ -234,4 +234,56 @@ int twin_steps(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, in
     return 0;
 }
 
+// The device-resident time loop of pyh_run, kernel for kernel: per step k_dt (CFL minimum + realizability, warp shuffles
+// and all) -> k_dt_finalize (clamp to t_final - t, dt * a[s][k] table, active flag) -> stages + ghost refreshes ->
+// k_step_end; every kernel early-exits once t >= t_final.  Outputs the dt sequence, the final time / step count / flag.
+int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int nt, int tys, double gamma, double cfl, int S,
+             const double* tab, double t0, double t_final, int max_steps, const double* nodes_x, const double* nodes_y, const double* area,
+             const double* cos_v, const double* sin_v, const double* cos_h, const double* sin_h, const int* nbr, const int* bc,
+             const int* is_cart, const double* dirichlet, const double* U, double* Uout, double* dts_out, double* t_out, int* nsteps_out,
+             int* bad_out) {
+    Twin T;
+    int rc = T.setup(flux, lim, prim, nq, nx, ny, nblk, nt, tys, gamma, S, tab, nodes_x, nodes_y, area, cos_v, sin_v, cos_h, sin_h, nbr, bc,
+                     is_cart, dirichlet, U);
+    if (rc) return rc;
+    Tableau tb;
+    std::memset(&tb, 0, sizeof(tb));
+    tb.nstages = S;
+    for (int i = 0; i < PYH_MAX_STAGES * PYH_MAX_STAGES; ++i) tb.a[i] = tab[i];
+    Control& ctl = T.ctl;
+    ctl.t = t0; ctl.t_final = t_final; ctl.dtmin_bits = DKEY_INF; ctl.active = 1; ctl.nsteps = 0; ctl.bad = 0;
+    ctl.dts = dts_out; ctl.dts_cap = max_steps;
+    int i0 = 0, i1 = 1, i2 = 2, cur = 0;
+    T.ghost(i0);
+    auto dt_kernel = [&](int buf, int respect_active) {   // launch_dt
+        launch(dim3(cdivu(nx, 256), cdivu(ny, DT_ROWS), nblk), 256, true,
+               [&] { k_dt(T.blks.data(), T.lay, T.po, T.po.H[buf], nblk, &ctl, T.C, respect_active); });
+    };
+    for (int n = 0; n < max_steps; ++n) {                 // enqueue_step
+        dt_kernel(i0, 1);
+        k_dt_finalize(&ctl, cfl, tb, 0, nullptr);
+        for (int s = 0; s < S; ++s) {
+            cur = (s == 0) ? i0 : cur;
+            const int next = plan_next_buffer(S, s, cur, i0, i1, i2);
+            T.stage(plan_stage(tab, S, T.po, i0, s, cur, next), 0);
+            cur = next;
+            if (s == S - 1) {
+                if (S == 1) std::swap(i0, i1);
+                cur = i0;
+            }
+            T.ghost(cur);
+        }
+        k_step_end(&ctl);
+        if (!ctl.active || ctl.bad || !(ctl.t < ctl.t_final)) break;
+    }
+    dt_kernel(i0, 0);                                     // final realizability check of the last state
+    double tmp = 0.0;
+    k_dt_finalize(&ctl, cfl, tb, 1, &tmp);
+    T.fetch_state(i0, Uout);
+    *t_out = ctl.t;
+    *nsteps_out = (int)ctl.nsteps;
+    *bad_out = ctl.bad;
+    return 0;
+}
+
 }  // extern "C"

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -60,7 +61,10 @@ static inline int rsq64h(int hi) { return __double2hiint(1.0 / std::sqrt(__hiloi
 // ---- CTA emulation for tests/host_twin/kernel_twin.cpp: the stage kernel itself runs on the host, one OS thread per
 // CUDA thread of a thread block, __syncthreads() == a std::barrier over the block; thread blocks run one after another.
 #define __launch_bounds__(...)
-#define __shared__
+// static __shared__ arrays become function-local statics: one copy shared by all threads, which is what they are inside a
+// thread block (blocks run one after another).  The stage kernel's dynamic `extern __shared__` array is declared through
+// PYH_HOST_TWIN in pyh_stage_march.cuh (an `extern static` does not exist).
+#define __shared__ static
 
 struct dim3 {
     unsigned x, y, z;
@@ -71,6 +75,9 @@ inline dim3 blockIdx, blockDim, gridDim;
 
 namespace pyh_host_twin {
 inline std::barrier<>* cta_barrier = nullptr;
+// warp shuffles: the 32 threads of a warp meet at their own barrier around an exchange buffer
+inline thread_local std::barrier<>* warp_barrier = nullptr;
+inline thread_local unsigned long long* warp_buf = nullptr;   // 32 slots of this thread's warp
 
 // run `body()` for every thread of every block of the grid; with_barrier spawns real threads (needed as soon as the
 // kernel calls __syncthreads), otherwise the threads of a block run one after another on the calling thread
@@ -87,13 +94,21 @@ inline void launch(dim3 grid, unsigned nthreads, bool with_barrier, const std::f
                 }
                 std::barrier<> bar((std::ptrdiff_t)nthreads);
                 cta_barrier = &bar;
+                const unsigned nwarps = (nthreads + 31) / 32;
+                std::vector<std::unique_ptr<std::barrier<>>> wbar;
+                for (unsigned w = 0; w < nwarps; ++w)
+                    wbar.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(32u, nthreads - 32 * w)));
+                std::vector<unsigned long long> wbuf(32 * (size_t)nwarps, 0ull);
                 std::vector<std::thread> th;
                 th.reserve(nthreads);
                 for (unsigned t = 0; t < nthreads; ++t)
-                    th.emplace_back([t, &body, &bar] {
+                    th.emplace_back([t, &body, &bar, &wbar, &wbuf] {
                         threadIdx = dim3(t);
+                        warp_barrier = wbar[t / 32].get();
+                        warp_buf = wbuf.data() + 32 * (size_t)(t / 32);
                         body();
                         bar.arrive_and_drop();   // a thread that returns early must not hold the others
+                        warp_barrier->arrive_and_drop();
                     });
                 for (auto& x : th) x.join();
                 cta_barrier = nullptr;
@@ -105,7 +120,19 @@ static inline void __syncthreads() { pyh_host_twin::cta_barrier->arrive_and_wait
 static inline void __threadfence() {}
 static inline void __nanosleep(unsigned) {}
 static inline double __longlong_as_double(long long b) { double x; std::memcpy(&x, &b, 8); return x; }
-// k_dt (warp shuffles) is compiled but never run by the twin
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { std::abort(); return v; }
+// full-warp butterfly exchange (every lane of the warp must call it, as in k_dt)
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle of up to 64 bits");
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    pyh_host_twin::warp_buf[lane] = bits;
+    pyh_host_twin::warp_barrier->arrive_and_wait();
+    const unsigned long long other = pyh_host_twin::warp_buf[lane ^ (unsigned)lane_mask];
+    pyh_host_twin::warp_barrier->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &other, sizeof(T));
+    return r;
+}
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }

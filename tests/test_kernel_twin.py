@@ -216,3 +216,64 @@ def test_shared_memory_protocol_of_the_stage_kernel_is_race_free_under_thread_sa
         pytest.skip("the interpreter does not run under a preloaded libtsan here: " + r.stderr[-300:])
     assert "TWIN-RUN-COMPLETE" in r.stdout, r.stderr[-2000:]
     assert "ThreadSanitizer: data race" not in r.stderr, r.stderr[:3000]
+
+
+def run_loop(lib, fx, t0, t_final, max_steps, nt=32, tys=64):
+    from pyhype_b200._lib import PYH_MAX_STAGES
+    from pyhype_b200.time_marching import TABLEAUX
+
+    nx, ny = fx.nx, fx.ny
+    idx, sch, nb, mlen, A, nbr, bc, cart, dirichlet, U = marshal(fx)
+    rows = TABLEAUX[sch["integrator"]]
+    tab = np.zeros(PYH_MAX_STAGES * PYH_MAX_STAGES)
+    for s_, row in enumerate(rows):
+        for k, a in enumerate(row):
+            tab[s_ * PYH_MAX_STAGES + k] = float(a)
+    Uout = np.empty_like(U)
+    dts = np.zeros(max_steps)
+    t = C.c_double(0.0)
+    nsteps, bad = C.c_int(0), C.c_int(0)
+    p = lambda a, ty=dp: a.ctypes.data_as(ty)
+    rc = lib.twin_run(FLUX[sch["flux"]], LIM[sch["limiter"]], int(sch["recon"] == "primitive"), int(sch["nqp"]), nx, ny, nb, nt, tys,
+                      C.c_double(fx.meta["gamma"]), C.c_double(sch["CFL"]), len(rows), p(tab), C.c_double(t0), C.c_double(t_final),
+                      max_steps, p(A["nodes_x"]), p(A["nodes_y"]), p(A["area"]), p(A["cos_v"]), p(A["sin_v"]), p(A["cos_h"]), p(A["sin_h"]),
+                      p(nbr, ip), p(bc, ip), p(cart, ip), p(dirichlet), p(U), p(Uout), p(dts), C.byref(t), C.byref(nsteps), C.byref(bad))
+    assert rc == 0
+    return idx, Uout, dts[: nsteps.value], t.value, nsteps.value, bad.value
+
+
+@pytest.mark.parametrize("name", ["em_roe_venkat_cons_rk4", "dmr_hlll_venkat_prim_rk2", "wedge_roe_cons_rk2", "jet_hlle_prim_rk2",
+                                  "em_int_ExplicitEuler1", "em_int_DormandPrince5"])
+def test_device_resident_time_loop_source_reproduces_dt_sequence_and_state(lib_default, name):
+    """pyh_run's loop, kernel for kernel, on the CPU: k_dt (the CFL reduction with its warp shuffles, shared-memory stage
+    and atomic minimum, quad_block.py:423-436), k_dt_finalize, the stages, k_step_end -- the reference's dt sequence and
+    final state, bit for bit."""
+    fx = golden_io.Fixture(name)
+    n = fx.meta["steps"]
+    idx, Uout, dts, t, nsteps, bad = run_loop(lib_default, fx, 0.0, 1e9, n)
+    assert nsteps == n and not bad
+    assert list(dts) == list(fx["dts"])
+    for g in fx.gids:
+        assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g)
+
+
+def test_device_resident_time_loop_source_clamps_dt_and_stops_at_t_final(lib_default):
+    fx = golden_io.Fixture("em_roe_venkat_cons_rk4")
+    ref = list(fx["dts"])
+    t_final = ref[0] + ref[1] + 0.25 * ref[2]
+    idx, Uout, dts, t, nsteps, bad = run_loop(lib_default, fx, 0.0, t_final, 16)
+    assert nsteps == 3 and not bad and list(dts[:2]) == ref[:2]
+    tt = 0.0 + ref[0]
+    tt += ref[1]
+    assert dts[2] == t_final - tt and t == tt + dts[2] and not (t < t_final)      # solvers/base.py:132-136
+
+
+def test_device_resident_time_loop_source_flags_unrealizable_states(lib_default):
+    fx = golden_io.Fixture("em_lim_VanLeer")
+    g0 = fx.gids[0]
+    U = fx.z[f"U0_{g0}"].copy()
+    U[3, 4, 0] = -1.0        # negative density (states/conservative.py:161-165)
+    fx.z = dict(fx.z)
+    fx.z[f"U0_{g0}"] = U
+    idx, Uout, dts, t, nsteps, bad = run_loop(lib_default, fx, 0.0, 1e9, 3)
+    assert bad and nsteps == 0

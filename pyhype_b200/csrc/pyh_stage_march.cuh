@@ -49,6 +49,12 @@ constexpr int kUnrollB1 = PYH_UNROLL_B1, kUnrollB2 = PYH_UNROLL_B2;   // (#pragm
 #ifndef PYH_SKIP_UNIT_ROT
 #define PYH_SKIP_UNIT_ROT 1
 #endif
+// PYH_D_EARLY (default 0, to be measured): phase D waits on its Runge-Kutta source loads right where it issues them (47 % of
+// its samples are long_scoreboard, profiles/r01s_summary.md).  1: issue the area and the source loads of the first two
+// targets at the top of D, ahead of the residual arithmetic; 2: ahead of the south-face Riemann solve.
+#ifndef PYH_D_EARLY
+#define PYH_D_EARLY 0
+#endif
 
 // PYH_COLD_HOOKS (default 0, to be measured): the test hooks of the kernel (gradient / limiter / residual stores for
 // pyh_debug_fetch and pyh_residual) are small enough for the compiler to predicate, so their address arithmetic is issued
@@ -388,6 +394,21 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 
         // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
+#if PYH_D_EARLY
+            double dA = 1.0, dS0[4] = {0.0, 0.0, 0.0, 0.0}, dS1[4] = {0.0, 0.0, 0.0, 0.0};
+            auto load_d = [&]() {
+                const unsigned om_ = o - pitch;
+                dA = G[po.A + om_];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dS0[k] = (plan.ntargets > 0) ? base[plan.t[0].src + k * PL + om_] : 0.0;
+                    dS1[k] = (plan.ntargets > 1) ? base[plan.t[1].src + k * PL + om_] : 0.0;
+                }
+            };
+#endif
+#if PYH_D_EARLY == 2
+            if (r - 1 >= i0) load_d();
+#endif
             const double cf = G[po.ch + o], sf = G[po.sh + o], Lf = G[po.Lh + o];
             const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;
             const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;
@@ -452,7 +473,14 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
             if (r - 1 >= i0) {
                 const unsigned om = o - pitch;
+#if PYH_D_EARLY == 1
+                load_d();
+#endif
+#if PYH_D_EARLY
+                const double a = dA;
+#else
                 const double a = G[po.A + om];
+#endif
                 double Rk[4];
                 auto resid = [&](auto tag) -> bool {
                     constexpr bool FAST = decltype(tag)::value;
@@ -486,8 +514,13 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     double s0[4], s1[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+#if PYH_D_EARLY
+                        s0[k] = dS0[k];
+                        s1[k] = dS1[k];
+#else
                         s0[k] = (nt_ > 0) ? base[plan.t[0].src + k * PL + om] : 0.0;
                         s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + om] : 0.0;
+#endif
                     }
                     if (nt_ > 0) {
                         const double c0 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[0].coef] : ctl->coef[plan.t[0].coef];

@@ -31,7 +31,9 @@ ip = C.POINTER(C.c_int)
 
 
 # extra -D flags of the builds that are checked: the shipped default and the opt-in variants waiting for GPU time
-BUILDS = {"default": [], "tight": ["-DPYH_LEAN_CHECKS=1", "-DPYH_COLD_HOOKS=1"], "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0"], "uniform_shortcut": ["-DPYH_UNIFORM_SHORTCUT=1"]}
+BUILDS = {"default": [], "tight": ["-DPYH_LEAN_CHECKS=1", "-DPYH_COLD_HOOKS=1", "-DPYH_D_EARLY=1"],
+          "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0"], "uniform_shortcut": ["-DPYH_UNIFORM_SHORTCUT=1"],
+          "d_early_unrolled": ["-DPYH_D_EARLY=2", "-DPYH_UNROLL_B1=2", "-DPYH_UNROLL_B2=2"]}
 
 
 def build(name):
@@ -162,8 +164,22 @@ def run_steps(lib, fx, nt, tys):
     return idx, Uout
 
 
-@pytest.mark.parametrize("name", golden_io.names())
-def test_whole_time_steps_of_the_kernel_source_match_reference_fixture(lib, name):
+STEP_SUBSET = ["em_roe_venkat_cons_rk4", "dmr_hlll_venkat_prim_rk2", "wedge_roe_cons_rk2", "jet_hlle_prim_rk2", "step_hlll_prim_rk2",
+               "em_int_DormandPrince5", "em_int_ExplicitEuler1", "em_nqp2"]
+
+
+@pytest.mark.parametrize("name", STEP_SUBSET)
+def test_whole_time_steps_of_every_build_match_reference_fixture(lib, name):
+    """The opt-in builds on a cross-section of the fixtures (all of them run on the default build below)."""
+    fx = golden_io.Fixture(name)
+    idx, Uout = run_steps(lib, fx, nt=32, tys=64)
+    for g in fx.gids:
+        assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g, np.abs(Uout[idx[g]] - fx[f"U_{g}"]).max())
+
+
+@pytest.mark.parametrize("name", [n for n in golden_io.names() if n not in STEP_SUBSET])
+def test_whole_time_steps_of_the_kernel_source_match_reference_fixture(lib_default, name):
+    lib = lib_default
     """Every stage of every step -- the product's plan logic (pyh_plan.cuh: buffer roles, running partial sums), the
     stage kernel and the ghost refresh in between -- with the reference's own dt sequence: the state after N steps is
     the reference's, bit for bit, for all ten tableaux."""

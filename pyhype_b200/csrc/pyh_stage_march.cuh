@@ -55,6 +55,13 @@ constexpr int kUnrollB1 = PYH_UNROLL_B1, kUnrollB2 = PYH_UNROLL_B2;   // (#pragm
 #ifndef PYH_D_EARLY
 #define PYH_D_EARLY 0
 #endif
+// PYH_B_GEOM_FIRST (default 0, to be measured): the 13 + 8 NQ geometry loads of phase B are issued at the very top of the
+// row iteration, ahead of the ring bookkeeping (publish row r+1, issue the state loads of row r+2: ~150 instructions that
+// need no geometry), instead of right in front of their first consumer, where 10 % of all warp samples wait on them
+// (profiles/r01s_summary.md).  Nothing but the loop-carried state is live at that point, so the registers are there.
+#ifndef PYH_B_GEOM_FIRST
+#define PYH_B_GEOM_FIRST 0
+#endif
 
 // PYH_COLD_HOOKS (default 0, to be measured): the test hooks of the kernel (gradient / limiter / residual stores for
 // pyh_debug_fetch and pyh_residual) are small enough for the compiler to predicate, so their address arithmetic is issued
@@ -190,6 +197,25 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         const bool full = (r >= i0) && (r < i1);           // rows this strip outputs
         const unsigned o = (unsigned)((r + 1) * pitch + PADL + jc);
 
+#if PYH_B_GEOM_FIRST
+        double gLE = 0.0, gLW = 0.0, gLN = 0.0, gLS = 0.0, gcE = 0.0, gcW = 0.0, gcN = 0.0, gcS = 0.0, gsE = 0.0, gsW = 0.0, gsN = 0.0, gsS = 0.0, gA = 1.0;
+        double gdx[NQ][4], gdy[NQ][4];
+        if (doB && (r < ny)) {
+            const unsigned oE = o + 1, oN = o + pitch;
+            gLE = G[po.Lv + oE]; gLW = G[po.Lv + o]; gLN = G[po.Lh + oN]; gLS = G[po.Lh + o];
+            gcE = G[po.cv + oE]; gcW = G[po.cv + o]; gcN = G[po.ch + oN]; gcS = G[po.ch + o];
+            gsE = G[po.sv + oE]; gsW = G[po.sv + o]; gsN = G[po.sh + oN]; gsS = G[po.sh + o];
+            gA = G[po.A + o];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    gdx[q][f] = G[po.dxy + ((q * 4 + f) * 2) * PL + o];
+                    gdy[q][f] = G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o];
+                }
+            }
+        }
+#endif
         // top: publish row r+1, issue the loads of row r+2 (L2 prefetch hints were measured and hurt: profiles/r01h_summary.md)
         to_recon(Qn);
         publish(sp, Qn);
@@ -204,6 +230,20 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             if (doB && rowreal) {
                 const unsigned oE = o + 1, oN = o + pitch;
                 // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155)
+#if PYH_B_GEOM_FIRST
+                (void)oE; (void)oN;
+                double LE = gLE, LW = gLW, LN = gLN, LS = gLS;
+#if PYH_FOLD_POW2
+                LE = 0.5 * LE; LW = 0.5 * LW; LN = 0.5 * LN; LS = 0.5 * LS;
+#endif
+                double xlE = LE * gcE, xlW = LW * (-gcW);
+                double xlN = LN * gcN, xlS = LS * (-gcS);
+                double ylE = LE * gsE, ylW = LW * (-gsW);
+                double ylN = LN * gsN, ylS = LS * (-gsS);
+                double Acell = gA;
+                double (&dx)[NQ][4] = gdx;
+                double (&dy)[NQ][4] = gdy;
+#else
                 double LE = G[po.Lv + oE], LW = G[po.Lv + o], LN = G[po.Lh + oN], LS = G[po.Lh + o];
 #if PYH_FOLD_POW2
                 // half face weights: (0.5 (q + qE)) * xlE == (q + qE) * (0.5 xlE), both scalings exact (pyh_math.cuh)
@@ -223,6 +263,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         dy[q][f] = G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o];
                     }
                 }
+#endif
                 bool okA = true;
                 double ia = Ar<true>::rcp(Acell, okA);
                 if (!okA) ia = 1.0 / Acell;

@@ -32,15 +32,15 @@ def _ptr(a, t=dp):
 
 
 class Twin:
-    def __init__(self, fold, lean=0, shortcut=0):
+    def __init__(self, fold, lean=0, shortcut=0, cert=0):
         os.makedirs(OUT, exist_ok=True)
-        lib = os.path.join(OUT, f"libpyh_twin_fold{fold}_lean{lean}_sc{shortcut}.so")
+        lib = os.path.join(OUT, f"libpyh_twin_fold{fold}_lean{lean}_sc{shortcut}_hc{cert}.so")
         deps = [SRC, os.path.join(SHIM, "cuda_runtime.h"), os.path.join(CSRC, "pyh_math.cuh"), os.path.join(CSRC, "pyh_fastdiv.cuh")]
         if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
             gxx = shutil.which("g++")
             if gxx is None:
                 pytest.skip("g++ not available")
-            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}", f"-DPYH_LEAN_CHECKS={lean}", f"-DPYH_UNIFORM_SHORTCUT={shortcut}",
+            subprocess.run([gxx, "-O2", "-ffp-contract=off", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DPYH_FOLD_POW2={fold}", f"-DPYH_LEAN_CHECKS={lean}", f"-DPYH_UNIFORM_SHORTCUT={shortcut}", f"-DPYH_HARTEN_CERT={cert}",
                             "-I", SHIM, "-I", CSRC, "-o", lib, SRC], check=True)
         self.lib = C.CDLL(lib)
         self.lib.twin_flux_scale.restype = C.c_double
@@ -89,8 +89,8 @@ class Twin:
 
 
 # (PYH_FOLD_POW2, PYH_LEAN_CHECKS, PYH_UNIFORM_SHORTCUT): the literal operation list, the shipped default, the opt-in builds
-@pytest.fixture(scope="module", params=[(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0, 1), (0, 0, 1)],
-                ids=["literal", "fold_pow2", "fold_pow2_lean", "fold_pow2_uniform", "literal_uniform"])
+@pytest.fixture(scope="module", params=[(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0, 1), (0, 0, 1), (1, 0, 0, 1), (1, 1, 1, 1)],
+                ids=["literal", "fold_pow2", "fold_pow2_lean", "fold_pow2_uniform", "literal_uniform", "harten_cert", "everything"])
 def twin(request):
     return Twin(*request.param)
 

@@ -33,7 +33,7 @@ ip = C.POINTER(C.c_int)
 # extra -D flags of the builds that are checked: the shipped default and the opt-in variants waiting for GPU time
 BUILDS = {"default": [], "tight": ["-DPYH_LEAN_CHECKS=1", "-DPYH_COLD_HOOKS=1", "-DPYH_D_EARLY=1"],
           "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0"], "uniform_shortcut": ["-DPYH_UNIFORM_SHORTCUT=1"],
-          "early_loads_unrolled_cert": ["-DPYH_D_EARLY=2", "-DPYH_B_GEOM_FIRST=1", "-DPYH_UNROLL_B1=2", "-DPYH_UNROLL_B2=2", "-DPYH_HARTEN_CERT=1"]}
+          "early_loads_unrolled_cert": ["-DPYH_D_EARLY=2", "-DPYH_B_GEOM_FIRST=1", "-DPYH_UNROLL_B1=2", "-DPYH_UNROLL_B2=2", "-DPYH_HARTEN_CERT=1", "-DPYH_MINMAX_NET=1"]}
 
 
 def build(name):

@@ -16,8 +16,9 @@ tools/build_variant.sh dearly2_b2x2 -DPYH_D_EARLY=2 -DPYH_UNROLL_B2=2
 tools/build_variant.sh geomfirst -DPYH_B_GEOM_FIRST=1
 tools/build_variant.sh geomfirst_dearly1 -DPYH_B_GEOM_FIRST=1 -DPYH_D_EARLY=1
 tools/build_variant.sh hcert -DPYH_HARTEN_CERT=1
+tools/build_variant.sh hcert_minmax -DPYH_HARTEN_CERT=1 -DPYH_MINMAX_NET=1
 tools/build_variant.sh uniform -DPYH_UNIFORM_SHORTCUT=1
 tools/build_variant.sh uniform_tight -DPYH_UNIFORM_SHORTCUT=1 -DPYH_LEAN_CHECKS=1 -DPYH_COLD_HOOKS=1
 echo
-echo "gpurun --timeout 600 -- 'tools/variant_bench.sh base tight b2x2 b2x4 b1x2_b2x2 dearly1 dearly2 dearly2_b2x2 geomfirst geomfirst_dearly1 hcert uniform uniform_tight \"base PYH_MARCH_NT=64\" \"geomfirst PYH_MARCH_NT=64\" base > gpurun_out/variants.txt 2>&1; \\"
+echo "gpurun --timeout 600 -- 'tools/variant_bench.sh base tight b2x2 b2x4 b1x2_b2x2 dearly1 dearly2 dearly2_b2x2 geomfirst geomfirst_dearly1 hcert hcert_minmax uniform uniform_tight \"base PYH_MARCH_NT=64\" \"geomfirst PYH_MARCH_NT=64\" base > gpurun_out/variants.txt 2>&1; \\"
 echo "  for v in base uniform; do PYH_LIB_PATH=\$PWD/gpurun_variants/libpyh_\$v.so python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 --ic smooth | tail -1 >> gpurun_out/variants_smooth.jsonl; done'"

@@ -1,0 +1,99 @@
+"""Fingerprints of BASELINE.json's NAMED configurations at their NAMED sizes, produced by running the
+UNMODIFIED reference (/root/reference, through oracle/refharness.py) in the build container.
+
+TEST INFRASTRUCTURE ONLY (see oracle/refharness.py).
+
+    python oracle/make_named_fingerprints.py em     # explosion_multi: 2x4 blocks of 150x150, Roe + Venkatakrishnan,
+                                                    # RK4, CFL 0.7 as shipped, from the initial condition to t_final = 0.07
+                                                    # (1604 steps; ~40 min of one core)
+    python oracle/make_named_fingerprints.py dmr    # DMR: 4 blocks of 500x500, HLLL + Venkatakrishnan, primitive
+                                                    # reconstruction, RK2, CFL 0.4, the first 40 steps (~10 min)
+
+The full states are too large to commit (5.8 MB / 32 MB), so each checkpoint stores, per block: the sha256 of the
+state BY VALUE (``(U + 0.0).tobytes()``: adding +0.0 maps -0.0 to +0.0, every other double to itself, so the digest
+is equal exactly when ``np.array_equal`` would be), a strided subsample of the state (for a readable diff when a
+digest differs) and the four sums; plus the complete dt sequence.  tests/test_gpu_named_configs.py replays the run
+on the GPU from the same initial condition and compares digest by digest; tests/test_oracle_golden.py does the
+same for the numpy restatement on the first checkpoint.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import refharness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "named")
+
+CASES = {
+    "em": dict(mesh="em_mesh", ic="explosion_ic", nx=150, ny=150, stride=15, checkpoints=[10, 50, 200, 600, 1200, -1],
+               cfg=dict(t_final=0.07),
+               what="examples/explosion_multi as shipped (CFL 0.7), initial condition -> t_final"),
+    "dmr": dict(mesh="dmr_mesh", ic="dmr_ic", nx=500, ny=500, stride=50, checkpoints=[5, 20, 40],
+                cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive",
+                         t_final=0.25),
+                what="examples/dmr scheme at BASELINE.json's 500x500 blocks (shipped: 50x50), first 40 steps"),
+}
+
+
+def value_digest(U):
+    return hashlib.sha256((np.ascontiguousarray(U) + 0.0).tobytes()).hexdigest()
+
+
+def main(name):
+    import cases
+    from make_golden import ref_blocks
+
+    c = CASES[name]
+    blocks = getattr(cases, c["mesh"])()
+    ic = getattr(cases, c["ic"])
+
+    class IC:
+        def apply_to_block(self, block):
+            block.state.data = np.ascontiguousarray(ic(block.mesh.x[:, :, 0], block.mesh.y[:, :, 0]))
+
+    config = rh.make_config(nx=c["nx"], ny=c["ny"], initial_condition=IC(), **c["cfg"])
+    run = rh.RefRun(config, ref_blocks(blocks))
+    t_final = float(run.solver.t_final)
+    out, meta = {}, dict(name=name, what=c["what"], nx=c["nx"], ny=c["ny"], stride=c["stride"], mesh=c["mesh"], ic=c["ic"],
+                         flux=config.fvm_flux_function_type, limiter=config.fvm_slope_limiter_type,
+                         recon=c["cfg"].get("reconstruction_type", "conservative"), integrator=config.time_integrator,
+                         CFL=config.CFL, t_final_nd=t_final, gids=sorted(blocks), checkpoints=[], digests={}, raw_sha16={},
+                         generator="oracle/make_named_fingerprints.py on the unmodified reference")
+    t0 = time.time()
+    for cp in c["checkpoints"]:
+        target = 10**9 if cp < 0 else cp
+        run.step(target - len(run.dts))
+        n = len(run.dts)
+        meta["checkpoints"].append(n)
+        sums = []
+        for blk in run.blocks:
+            g = blk.global_block_num
+            U = blk.state.data
+            meta["digests"][f"{n}_{g}"] = value_digest(U)
+            meta["raw_sha16"][f"{n}_{g}"] = hashlib.sha256(U.tobytes()).hexdigest()[:16]   # SURVEY.md section 8c's form
+            out[f"sub_{n}_{g}"] = U[:: c["stride"], :: c["stride"]].copy()
+            sums.append(U.sum(axis=(0, 1)))
+        out[f"sums_{n}"] = np.array(sums)
+        print(f"[{name}] step {n}  t = {run.solver.t:.6f} / {t_final:.6f}  ({time.time() - t0:.0f} s)", flush=True)
+    meta["t_end"] = float(run.solver.t)
+    meta["reached_t_final"] = not (run.solver.t < t_final)
+    out["dts"] = np.array(run.dts)
+    out["meta"] = np.array(json.dumps(meta))
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -1,0 +1,119 @@
+"""BASELINE.json's named configurations at their NAMED sizes against fingerprints of the unmodified reference
+(tests/golden/named/*.npz, written by oracle/make_named_fingerprints.py in the build container):
+
+* explosion_multi exactly as shipped -- 2 x 4 blocks of 150 x 150, Roe + Venkatakrishnan + Green-Gauss, RK4, CFL 0.7,
+  reflection walls -- from the initial condition to t_final = 0.07 (1604 steps);
+* the DMR scheme -- HLLL + Venkatakrishnan, primitive reconstruction, RK2, CFL 0.4 -- on 4 blocks of 500 x 500, the
+  first 40 steps.
+
+The reference's full states are too large to commit, so a fingerprint holds per checkpoint and block the sha256 of the
+state BY VALUE (-0.0 folded onto +0.0: equal digests <=> np.array_equal), a strided subsample and the complete dt
+sequence.  -m gpu: the CUDA engine replays the whole run through the C ABI and must reproduce every dt and every
+digest (the 1e-10 tolerance of the north star is asserted on the subsample as well, so that a digest mismatch reports how
+far off it is).  -m "not gpu": the numpy restatement (oracle/) and the CPU twin of the stage kernel's source on the
+first checkpoint."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+NAMED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "named")
+
+
+def value_digest(U):
+    return hashlib.sha256((np.ascontiguousarray(U) + 0.0).tobytes()).hexdigest()
+
+
+class Named:
+    """A fingerprint file; quacks like golden_io.Fixture where tests/test_kernel_twin.py needs it to."""
+
+    def __init__(self, name):
+        path = os.path.join(NAMED, name + ".npz")
+        if not os.path.exists(path):
+            pytest.skip(f"{path} not generated (oracle/make_named_fingerprints.py {name})")
+        self.z = np.load(path)
+        self.meta = dict(json.loads(str(self.z["meta"])), gamma=cases.GAMMA)
+        self.name = name
+        self.gids = self.meta["gids"]
+        self.nx, self.ny, self.stride = self.meta["nx"], self.meta["ny"], self.meta["stride"]
+        self.blocks = getattr(cases, self.meta["mesh"])()
+        self.ic = getattr(cases, self.meta["ic"])
+        self.dts = self.z["dts"]
+        self._u0 = None
+
+    def scheme(self):
+        m = self.meta
+        return dict(flux=m["flux"], limiter=m["limiter"], recon=m["recon"], integrator=m["integrator"], CFL=m["CFL"], nqp=1)
+
+    def __getitem__(self, key):           # U0_<gid> for the kernel twin's marshalling
+        if key.startswith("U0_"):
+            from pyhype_b200.mesh.quad_mesh import QuadMesh
+
+            b = self.blocks[int(key[3:])]
+            m = QuadMesh(self.nx, self.ny, NE=b["NE"], NW=b["NW"], SE=b["SE"], SW=b["SW"])
+            return np.ascontiguousarray(self.ic(m.x[:, :, 0], m.y[:, :, 0]))
+        return self.z[key]
+
+    def check(self, n, states):
+        """states: {gid: (ny, nx, 4)} after n steps"""
+        for g in self.gids:
+            U = states[g]
+            sub, ref = U[:: self.stride, :: self.stride], self.z[f"sub_{n}_{g}"]
+            for k in range(4):
+                scale = max(np.abs(ref[..., k]).max(), 1e-300)
+                assert np.abs(sub[..., k] - ref[..., k]).max() / scale <= 1e-10, (self.name, n, g, k)
+            assert value_digest(U) == self.meta["digests"][f"{n}_{g}"], (self.name, n, g, np.abs(sub - ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["em", "dmr"])
+def test_named_config_at_named_size_reproduces_the_reference(name):
+    fp = Named(name)
+    eng = cases.build_engine(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
+    try:
+        done_total, t = 0, 0.0
+        for n in fp.meta["checkpoints"]:
+            k = n - done_total
+            t, done, bad, dts = eng.run(t, fp.meta["t_final_nd"], max_steps=k, poll_every=16, record_dts=k)
+            assert done == k and not bad, (name, n, done)
+            assert np.array_equal(np.asarray(dts), fp.dts[done_total:n]), (name, n)
+            done_total = n
+            fp.check(n, {g: eng.download(g) for g in fp.gids})
+        assert t == fp.meta["t_end"]
+        if fp.meta["reached_t_final"]:
+            assert not (t < fp.meta["t_final_nd"])
+            assert eng.run(t, fp.meta["t_final_nd"], max_steps=4, poll_every=1)[1] == 0      # the run is over: no further step
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["em", "dmr"])
+def test_oracle_restatement_at_named_size_first_checkpoint(name):
+    fp = Named(name)
+    n = fp.meta["checkpoints"][0]
+    prob = cases.build_oracle(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
+    t, dts = prob.run(0.0, fp.meta["t_final_nd"], max_steps=n)
+    assert np.array_equal(np.asarray(dts), fp.dts[:n])
+    fp.check(n, {g: prob.blocks[g].U for g in fp.gids})
+
+
+@pytest.mark.parametrize("name", ["em", "dmr"])
+def test_stage_kernel_source_twin_at_named_size_first_checkpoint(name):
+    """The device-resident time loop of the product (k_dt, k_dt_finalize, k_stage_march in the shipped 128-thread x 64-row
+    strip shape, k_ghost, k_step_end), compiled by g++ and run by the thread-block emulator of tests/host_twin/, at the named
+    size: two column strips and three row strips per 150 x 150 block, four by eight per 500 x 500 block.  The DMR case
+    takes two minutes of emulation and runs only with PYH_NAMED_TWIN_ALL=1 (last run: profiles/r01u_named_config_parity.md)."""
+    if name == "dmr" and not os.environ.get("PYH_NAMED_TWIN_ALL"):
+        pytest.skip("two minutes of emulation: set PYH_NAMED_TWIN_ALL=1")
+    import test_kernel_twin as T
+
+    fp = Named(name)
+    n = fp.meta["checkpoints"][0]
+    idx, Uout, dts, t, nsteps, bad = T.run_loop(T.build("default"), fp, 0.0, fp.meta["t_final_nd"], n, nt=128, tys=64)
+    assert nsteps == n and not bad
+    assert np.array_equal(dts, fp.dts[:n])
+    fp.check(n, {g: Uout[idx[g]] for g in fp.gids})

@@ -5,6 +5,7 @@ reference (tests/golden/named/, oracle/make_named_fingerprints.py) -- longer tha
     python tools/named_replay.py oracle em          # the numpy restatement, every checkpoint up to t_final (~35 min)
     python tools/named_replay.py twin em 200        # the stage kernel's source on the thread-block emulator, 200 steps (~20 min)
     python tools/named_replay.py twin dmr 20
+    python tools/named_replay.py twin em 50 uniform_shortcut      # an opt-in build of tests/test_kernel_twin.py BUILDS
 
 Test infrastructure (it runs oracle/ and tests/host_twin/); results of the last runs: profiles/r01u_named_config_parity.md."""
 import os
@@ -41,12 +42,13 @@ def main():
         import test_kernel_twin as T
 
         n = int(sys.argv[3])
+        build = sys.argv[4] if len(sys.argv) > 4 else "default"     # a key of tests/test_kernel_twin.py BUILDS (opt-in variants)
         assert n in fp.meta["checkpoints"], fp.meta["checkpoints"]
-        idx, Uout, dts, t, nsteps, bad = T.run_loop(T.build("default"), fp, 0.0, fp.meta["t_final_nd"], n, nt=128, tys=64)
+        idx, Uout, dts, t, nsteps, bad = T.run_loop(T.build(build), fp, 0.0, fp.meta["t_final_nd"], n, nt=128, tys=64)
         assert nsteps == n and not bad
         assert np.array_equal(dts, fp.dts[:n]), ("dt sequence differs", name, n)
         fp.check(n, {g: Uout[idx[g]] for g in fp.gids})
-        print(f"kernel twin == reference: {name}, step {n} ({time.time() - t0:.0f} s)", flush=True)
+        print(f"kernel twin ({build} build) == reference: {name}, step {n} ({time.time() - t0:.0f} s)", flush=True)
     else:
         raise SystemExit(__doc__)
 

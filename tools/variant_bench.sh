@@ -10,4 +10,9 @@ for spec in "$@"; do
 try:
     d=json.loads(sys.stdin.read()); print("value %.4g ms/step %.3f stage_ms %.4f" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_avg"]))
 except Exception as e: print("FAILED", e)')"
+  # bit parity of the variant on explosion_multi at its named size, initial condition -> t_final (1604 steps, fingerprints of
+  # the unmodified reference; the bench-only libraries hold exactly this scheme); set PYH_VARIANT_PARITY=0 to skip
+  if [ "${PYH_VARIANT_PARITY:-1}" != 0 ]; then
+    env "$@" PYH_LIB_PATH=$PWD/gpurun_variants/libpyh_${name}.so python -m pytest tests/test_named_configs.py -m gpu -k em -q 2>&1 | tail -1 | sed "s/^/    named-size parity: /"
+  fi
 done

@@ -71,6 +71,9 @@ def ws_ic_smooth(x, y, width, height):
 
 
 BYTES_PER_CELL_STEP = {"RK4": 512.0, "RK2": 160.0, "ExplicitEuler1": 64.0}
+# FP64 instructions (DFMA + DMUL + DADD + DSETP) per cell-stage of the headline scheme, counted by ncu on the shipped build
+# (profiles/: r01s 1152 with the exact power-of-two scalings folded; the literal operation list of SURVEY.md section 8A needs 1187)
+FP64_INSTR_PER_CELL_STAGE = 1152
 
 
 def load_peaks():
@@ -159,13 +162,187 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
-def run_ours(args):
-    import torch
+def value_digest(U):
+    """sha256 of a state BY VALUE (-0.0 folded onto +0.0), the form tests/golden/named/*.npz store"""
+    import hashlib
 
-    from pyhype_b200.distributed import HaloExchanger, advance, distribute_blocks, world
+    return hashlib.sha256((np.ascontiguousarray(U) + 0.0).tobytes()).hexdigest()
+
+
+def build_engine(blocks, mine, nx, ny, scheme, device, ic=None, pin=False, timing=None):
+    """Engine with the local blocks `mine` of the block dictionary `blocks`; returns (engine, {gid: host state}).
+    scheme: dict(flux, limiter, recon, integrator, CFL).  Host geometry is built in parallel threads (numpy-bound)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from pyhype_b200.engine import Engine, SIDES
     from pyhype_b200.mesh.quad_mesh import QuadMesh
     from pyhype_b200.time_marching import get_tableau
+
+    tab = get_tableau(scheme["integrator"])
+    eng = Engine(nx, ny, scheme["flux"], scheme.get("limiter", "Venkatakrishnan"), scheme["recon"], tab, GAMMA, scheme["CFL"], device=device)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(mine)))) as pool:
+        meshes = dict(zip(mine, pool.map(lambda g: QuadMesh(nx, ny, NE=blocks[g]["NE"], NW=blocks[g]["NW"], SE=blocks[g]["SE"], SW=blocks[g]["SW"]), mine)))
+    t1 = time.perf_counter()
+    states = {}
+    for gid in mine:
+        b = blocks[gid]
+        m = meshes.pop(gid)
+        eng.add_block(gid, m, {s: b["Neighbor" + s] for s in SIDES}, {s: b["BCType" + s] for s in SIDES}, local_gids=set(mine))
+        if ic is not None:
+            U = np.ascontiguousarray(ic(m.x[:, :, 0], m.y[:, :, 0]))
+            if pin:
+                buf = eng.pinned_state_buffer()
+                buf[...] = U
+                U = buf
+            states[gid] = U
+        del m
+    eng.finalize()
+    if timing is not None:
+        timing["host_geometry_s"] = t1 - t0
+        timing["add_blocks_and_ic_s"] = time.perf_counter() - t1
+    return eng, states, len(tab)
+
+
+class StreamTimer:
+    """CUDA events on the engine's own stream (torch.cuda.Event only sees torch's current stream)."""
+
+    def __init__(self, torch, eng, device):
+        self.torch = torch
+        self.stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", device))
+
+    def event(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.stream)
+        return e
+
+
+def selfcheck_sharded(torch, dist, rank, wsize, lrank, args):
+    """The sharded run must produce the single-GPU bits: the weak-scaling grid at a tiny block size, a few time steps on
+    `wsize` ranks through pyh_run (NCCL strip exchange + dt all-reduce inside), every block's state digest gathered on
+    rank 0 and compared with the same run done on rank 0's GPU alone (all blocks local).  That single-GPU path is what
+    the -m gpu suite pins to the reference."""
+    from pyhype_b200.distributed import distribute_blocks, share_unique_id
+    from pyhype_b200.engine import Engine
+
+    nb, n, steps = args.blocks_per_gpu, 48, 6
+    blocks = ws_mesh(wsize, nb)
+    owner = distribute_blocks(len(blocks), wsize)
+    mine = sorted(g for g, r in owner.items() if r == rank)
+    width, height = BLOCK_LEN * nb, BLOCK_LEN * wsize
+    scheme = dict(flux=args.flux, recon=args.recon, integrator=args.integrator, CFL=0.7)
+    ic = lambda x, y: ws_ic(x, y, width, height) + 0.05 * (ws_ic_smooth(x, y, width, height) - ws_ic_smooth(0 * x, 0 * y, width, height))  # noqa: E731
+    eng, states, _ = build_engine(blocks, mine, n, n, scheme, lrank, ic=ic)
+    eng.comm_init(rank, wsize, share_unique_id(Engine.comm_unique_id, rank, wsize), owner)
+    for g in mine:
+        eng.upload(g, states[g])
+    eng.apply_bc()
+    t, nsteps, bad, dts = eng.run(0.0, 1e9, max_steps=steps, poll_every=4, record_dts=steps)
+    mine_dig = {g: value_digest(eng.download(g)) for g in mine}
+    eng.close()
+    gathered = [None] * wsize
+    dist.gather_object((mine_dig, list(dts), nsteps, bool(bad)), gathered if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    ref, rstates, _ = build_engine(blocks, sorted(blocks), n, n, scheme, lrank, ic=ic)
+    for g in sorted(blocks):
+        ref.upload(g, rstates[g])
+    ref.apply_bc()
+    t1, n1, bad1, dts1 = ref.run(0.0, 1e9, max_steps=steps, poll_every=4, record_dts=steps)
+    ref_dig = {g: value_digest(ref.download(g)) for g in sorted(blocks)}
+    ref.close()
+    ok, seen = True, {}
+    for dig, d, ns, b in gathered:
+        seen.update(dig)
+        ok = ok and d == list(dts1) and ns == n1 and not b
+    ok = ok and seen == ref_dig and not bad1
+    return {"sharded_equals_single_gpu": bool(ok), "ranks": wsize, "blocks": len(blocks), "block": n, "steps": steps,
+            "what": "per-block sha256 of the state by value + the dt sequence, N ranks vs one GPU"}
+
+
+NAMED = {
+    # BASELINE.json configs[0]: examples/explosion_multi exactly as shipped (config.py:8-34; CFL 0.7)
+    "explosion_multi": dict(fingerprint="em", title="examples/explosion_multi: 2x4 blocks of 150x150, Roe + Venkatakrishnan + GreenGauss, RK4, CFL 0.7 (as shipped), reflection BCs, t_final=0.07"),
+    # BASELINE.json configs[1]: the DMR scheme (examples/dmr/config.py:8-33) at the README's 500x500 blocks; the shipped mesh has 4 blocks
+    "dmr": dict(fingerprint="dmr", title="examples/dmr: Mach 10 double Mach reflection, 4 blocks (as shipped) of 500x500, HLLL + Venkatakrishnan, primitive reconstruction, RK2 (midpoint, the factory's SSP-RK2 stand-in), CFL 0.4"),
+}
+
+
+def run_named(torch, name, device, steps, peak):
+    """One of the reference's own named configurations at its named size on one GPU, through the device-resident loop
+    (pyh_run), replayed against the fingerprints of the unmodified reference (tests/golden/named/*.npz: data files written
+    by oracle/make_named_fingerprints.py; no oracle code runs here)."""
+    from pyhype_b200 import examples as ex
+
+    fpz = np.load(os.path.join(ROOT, "tests", "golden", "named", NAMED[name]["fingerprint"] + ".npz"))
+    meta = json.loads(str(fpz["meta"]))
+    blocks = getattr(ex, meta["mesh"])(*meta.get("mesh_args", []))
+    ic = getattr(ex, meta["ic"])
+    nx, ny = meta["nx"], meta["ny"]
+    scheme = dict(flux=meta["flux"], limiter=meta["limiter"], recon=meta["recon"], integrator=meta["integrator"], CFL=meta["CFL"])
+    gids = sorted(blocks)
+    eng, states, nstages = build_engine(blocks, gids, nx, ny, scheme, device, ic=ic, pin=True)
+    cells = len(gids) * nx * ny
+    timer = StreamTimer(torch, eng, device)
+
+    def load_ic():
+        for g in gids:
+            eng.upload(g, states[g])
+        eng.apply_bc()
+
+    # 1) parity replay (also the warm-up: captures the CUDA graph of one step)
+    load_ic()
+    done, t, parity_ok = 0, 0.0, True
+    for n in meta["checkpoints"]:
+        t, k, bad, dts = eng.run(t, meta["t_final_nd"], max_steps=n - done, poll_every=64, record_dts=n - done)
+        parity_ok = parity_ok and (k == n - done) and not bad and np.array_equal(np.asarray(dts), fpz["dts"][done:n])
+        done = n
+        for g in gids:
+            parity_ok = parity_ok and value_digest(eng.download(g)) == meta["digests"][f"{n}_{g}"]
+    # 2) timed: the same run again from the initial condition, `steps` steps (0 = as far as the fingerprint goes)
+    K = min(steps, done) if steps > 0 else done
+    load_ic()
+    eng.sync()
+    l0 = eng.launch_count()
+    e0 = timer.event()
+    t, k, bad, _ = eng.run(0.0, meta["t_final_nd"], max_steps=K, poll_every=max(K, 1))
+    e1 = timer.event()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    # 3) end to end: host state in (pinned) -> H2D -> ghost refresh -> K steps -> D2H into pinned host buffers
+    outs = {g: eng.pinned_state_buffer() for g in gids}
+    t0 = time.perf_counter()
+    for g in gids:
+        eng.upload_async(g, states[g])
+    eng.commit_uploads()
+    eng.apply_bc()
+    eng.run(0.0, meta["t_final_nd"], max_steps=K, poll_every=max(K, 1))
+    for g in gids:
+        eng.download_async(g, outs[g])
+    eng.transfers_sync()
+    e2e_s = time.perf_counter() - t0
+    eng.close()
+    value = cells * nstages * k / (ms * 1e-3)
+    bpcs = BYTES_PER_CELL_STEP.get(meta["integrator"], 128.0 * nstages) / nstages
+    return {
+        "workload": NAMED[name]["title"], "cells_total": cells, "stages_per_step": nstages, "steps": int(k),
+        "value": value, "unit": "cell-stage updates/s", "ms_per_step": ms / max(k, 1), "gpu_launches": int(launches),
+        "parity": {"bit_identical_to_reference": bool(parity_ok), "checkpoints": meta["checkpoints"],
+                   "what": "every dt and the sha256-by-value of every block state at each checkpoint vs the unmodified reference's fingerprint (" + meta["generator"] + ")"},
+        "e2e": {"value": cells * nstages * k / e2e_s, "unit": "cell-stage updates/s", "h2d_bytes_per_step": cells * 32 / max(k, 1),
+                "d2h_bytes_per_step": cells * 32 / max(k, 1), "how": f"one job = upload the initial state from pinned host memory, ghost refresh, {int(k)} steps in the device-resident loop, download the state; bytes averaged over the steps"},
+        "roofline": {"bound": "hbm", "achieved": value * bpcs / 1e9, "peak": peak, "unit": "GB/s", "frac": value * bpcs / 1e9 / peak, "traffic": None,
+                     "algorithmic_bytes_per_cell_stage": bpcs,
+                     "note": "whole-step rate (all kernels of the captured step graph), not a single launch: a stage launch covers only %d cells here (%.2f waves of 592 resident thread blocks)" % (cells, cells / (124.0 * 64 * 592))},
+    }
+
+
+def run_ours(args):
+    import torch
+
+    from pyhype_b200.distributed import distribute_blocks, share_unique_id, world
+    from pyhype_b200.engine import Engine
 
     rank, wsize, lrank = world()
     n_gpus = args.gpus
@@ -177,136 +354,140 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(lrank)
     prev_affinity = bind_to_gpu_numa_node(lrank)
+    peak, peak_src = load_peaks()
     dist = None
     if wsize > 1:
         import torch.distributed as dist
 
-        from pyhype_b200.distributed import init_nccl
+        # control plane only (barriers, the max over ranks, the NCCL id): the data path is the library's own communicator
+        dist.init_process_group("gloo", rank=rank, world_size=wsize)
 
-        init_nccl(lrank)
+    if args.config != "ws":   # one of the reference's own small configurations as the main line (single GPU)
+        if wsize > 1:
+            raise SystemExit("--config explosion_multi|dmr are single-GPU lines (8 and 4 small blocks)")
+        sampler = ClockSampler(lrank)
+        sampler.start()
+        r = run_named(torch, args.config, lrank, args.steps if args.steps_given else 0, peak)
+        clocks = sampler.stop()
+        out = {"metric": "cell-stage updates/sec", "value": r["value"], "unit": r["unit"], "n_gpus": 1, "steps": r["steps"], "warmup": args.warmup,
+               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": r["workload"], "cells_total": r["cells_total"], "stages_per_step": r["stages_per_step"], "parity": r["parity"],
+                          "l2_policy": "state (%.1f MB) fits the 126 MB L2: this is the reference's own size" % (r["cells_total"] * 32 / 1e6)},
+               "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": dict(r["roofline"], peak_source=peak_src)}
+        print(json.dumps(out), flush=True)
+        return
+
+    selfcheck = None
+    if wsize > 1 and not args.no_selfcheck:
+        selfcheck = selfcheck_sharded(torch, dist, rank, wsize, lrank, args)
 
     nb, n = args.blocks_per_gpu, args.block
     integ = args.integrator
-    tab = get_tableau(integ)
-    nstages = len(tab)
     blocks = ws_mesh(n_gpus, nb)
     owner = distribute_blocks(len(blocks), wsize)
     mine = sorted(g for g, r in owner.items() if r == rank)
     width, height = BLOCK_LEN * nb, BLOCK_LEN * n_gpus
-
-    eng = Engine(n, n, args.flux, "Venkatakrishnan", args.recon, tab, GAMMA, 0.7, device=lrank)
-    host_states = {}
-    from concurrent.futures import ThreadPoolExecutor
-
-    with ThreadPoolExecutor(max_workers=min(8, max(1, len(mine)))) as pool:   # host geometry: numpy-bound, releases the GIL
-        meshes = dict(zip(mine, pool.map(lambda g: QuadMesh(n, n, NE=blocks[g]["NE"], NW=blocks[g]["NW"], SE=blocks[g]["SE"], SW=blocks[g]["SW"]), mine)))
-    for gid in mine:
-        b = blocks[gid]
-        m = meshes.pop(gid)
-        eng.add_block(gid, m, {s: b["Neighbor" + s] for s in SIDES}, {s: b["BCType" + s] for s in SIDES}, local_gids=set(mine))
-        U = (ws_ic_smooth if args.ic == "smooth" else ws_ic)(m.x[:, :, 0], m.y[:, :, 0], width, height)
-        pinned = torch.empty((n, n, 4), dtype=torch.float64, pin_memory=True)
-        pinned.numpy()[...] = U
-        host_states[gid] = pinned
-        del m, U
-    eng.finalize()
-    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", lrank))
-    hx = HaloExchanger(eng, owner, rank) if wsize > 1 else None
-
-    def upload_all():
-        for gid in mine:
-            eng.upload(gid, host_states[gid].numpy())
-
-    def refresh_ghosts():
-        if hx is not None:
-            hx.exchange()
-        eng.apply_bc()
-
-    def one_step():
-        """get_dt + integrate (Euler2D._solve body, pyhype/solvers/Euler2D.py:199-204), dt stays on the device"""
-        if hx is not None:
-            ptr = hx.global_dt().data_ptr()
-        else:
-            eng.local_dt(dt_dev.data_ptr())
-            ptr = dt_dev.data_ptr()
-        advance(eng, hx, nstages, dt_dev_ptr=ptr)
+    scheme = dict(flux=args.flux, recon=args.recon, integrator=integ, CFL=0.7)
+    setup = {}
+    ic = (lambda x, y: ws_ic_smooth(x, y, width, height)) if args.ic == "smooth" else (lambda x, y: ws_ic(x, y, width, height))
+    eng, host_states, nstages = build_engine(blocks, mine, n, n, scheme, lrank, ic=ic, pin=True, timing=setup)
+    if wsize > 1:
+        eng.comm_init(rank, wsize, share_unique_id(Engine.comm_unique_id, rank, wsize), owner)
+    timer = StreamTimer(torch, eng, lrank)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        dt_dev = torch.zeros(1, dtype=torch.float64, device=f"cuda:{lrank}")
-        upload_all()
-        refresh_ghosts()
-        for _ in range(args.warmup):
-            one_step()
+    t0 = time.perf_counter()
+    for gid in mine:
+        eng.upload(gid, host_states[gid])
+    eng.apply_bc()
+    eng.sync()
+    setup["upload_s"] = time.perf_counter() - t0
+
+    # ---- device-timed region: exactly K steps of the loop Euler2D._solve runs (pyh_run: CFL reduction [+ all-reduce], stages,
+    # [strip exchange,] ghost refresh; one captured CUDA graph per step), state resident in HBM
+    t, _, bad, _ = eng.run(0.0, 1e9, max_steps=args.warmup, poll_every=args.warmup)
+    barrier()
+    sampler = ClockSampler(lrank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    e0 = timer.event()
+    t, k, bad, _ = eng.run(t, 1e9, max_steps=args.steps, poll_every=args.steps)
+    e1 = timer.event()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    assert k == args.steps, (k, args.steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ok = eng.realizable()
+
+    # ---- the dominant kernel alone: events on the launching stream around every stage launch of two more steps
+    dt_dev = torch.zeros(1, dtype=torch.float64, device=f"cuda:{lrank}")
+    stage_ev = []
+    for _ in range(2):
+        eng.local_dt(dt_dev.data_ptr())
+        eng.step_begin_dev(dt_dev.data_ptr())
+        for s in range(nstages):
+            a = timer.event(); eng.stage(s); b_ = timer.event()
+            eng.apply_bc()
+            stage_ev.append((a, b_))
+    torch.cuda.synchronize()
+    stage_ms = [a.elapsed_time(b_) for a, b_ in stage_ev]
+
+    # ---- sustained window: a second, long timed region (>= 5 s at the default size) with the clock sampler on
+    sustained = None
+    if args.sustain_steps > 0:
         barrier()
-        sampler = ClockSampler(lrank)
+        s2 = ClockSampler(lrank)
         if rank == 0:
-            sampler.start()
-        l0 = eng.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            one_step()
-        e1.record(stream)
+            s2.start()
+        f0 = timer.event()
+        t, k2, bad2, _ = eng.run(t, 1e9, max_steps=args.sustain_steps, poll_every=args.sustain_steps)
+        f1 = timer.event()
         barrier()
-        ms = e0.elapsed_time(e1)
-        launches = eng.launch_count() - l0
-        clocks = sampler.stop() if rank == 0 else None
-        ok = eng.realizable()
+        sus_ms = f0.elapsed_time(f1)
+        sus_clocks = s2.stop() if rank == 0 else None
+        sustained = (sus_ms, int(k2), sus_clocks)
 
-        # per-kernel timing of the dominant (stage) kernel, live, with events on the launching stream
-        stage_ms = []
-        for _ in range(2):
-            if hx is not None:
-                eng.step_begin_dev(hx.global_dt().data_ptr())
-            else:
-                eng.local_dt(dt_dev.data_ptr()); eng.step_begin_dev(dt_dev.data_ptr())
-            for s in range(nstages):
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream); eng.stage(s); b_.record(stream)
-                refresh_ghosts()
-                stage_ms.append((a, b_))
-        torch.cuda.synchronize()
-        stage_ms = [a.elapsed_time(b_) for a, b_ in stage_ms]
+    # ---- end to end through the host-buffer API: EVERY step uploads its input state from pinned host memory, refreshes the
+    # ghosts, advances one time step (pyh_run, 1 step) and reads the result back into pinned host memory.  The steps are
+    # independent jobs, so the streaming entry points overlap the H2D copy of step n+1 and the D2H copy of step n-1 with the
+    # compute of step n (three streams).
+    e2e_steps = max(1, args.e2e_steps)
+    out_host = {gid: eng.pinned_state_buffer() for gid in mine}
 
-        # end-to-end through the host-buffer API: EVERY step uploads its input state from pinned host
-        # memory, refreshes the ghosts, advances one time step and reads the result back into pinned
-        # host memory.  The steps are independent jobs, so the streaming entry points overlap the H2D
-        # copy of step n+1 and the D2H copy of step n-1 with the compute of step n (three streams).
-        e2e_steps = max(1, args.e2e_steps)
-        out_host = {gid: torch.empty((n, n, 4), dtype=torch.float64, pin_memory=True).numpy() for gid in mine}
-        in_host = {gid: host_states[gid].numpy() for gid in mine}
+    def stage_inputs():
+        for gid in mine:
+            eng.upload_async(gid, host_states[gid])
 
-        def stage_inputs():
-            for gid in mine:
-                eng.upload_async(gid, in_host[gid])
-
-        barrier()
-        t0 = time.perf_counter()
-        stage_inputs()
-        for i in range(e2e_steps):
-            eng.commit_uploads()
-            if i + 1 < e2e_steps:
-                stage_inputs()          # waits (on the copy stream) until the conversion above has consumed the staging area
-            refresh_ghosts()
-            one_step()
-            for gid in mine:
-                eng.download_async(gid, out_host[gid])
-        eng.transfers_sync()
-        barrier()
-        e2e_s = time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    stage_inputs()
+    for i in range(e2e_steps):
+        eng.commit_uploads()
+        if i + 1 < e2e_steps:
+            stage_inputs()          # waits (on the copy stream) until the conversion above has consumed the staging area
+        eng.apply_bc()
+        eng.run(0.0, 1e9, max_steps=1, poll_every=1)
+        for gid in mine:
+            eng.download_async(gid, out_host[gid])
+    eng.transfers_sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    eng.close()
 
     # max over ranks
     cells_local = len(mine) * n * n
+    sus_ms = sustained[0] if sustained else 0.0
     if dist is not None:
-        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=f"cuda:{lrank}")
+        tt = torch.tensor([ms, e2e_s, sus_ms], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(tt[0]), float(tt[1])
-        cc = torch.tensor([cells_local, launches], dtype=torch.float64, device=f"cuda:{lrank}")
+        ms, e2e_s, sus_ms = float(tt[0]), float(tt[1]), float(tt[2])
+        cc = torch.tensor([cells_local, launches], dtype=torch.float64)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         cells_total, launches_total = int(cc[0]), int(cc[1])
     else:
@@ -317,21 +498,22 @@ def run_ours(args):
         return
     value = cells_total * nstages * args.steps / (ms * 1e-3)
     e2e_value = cells_total * nstages * e2e_steps / e2e_s
-    peak, peak_src = load_peaks()
     bytes_per_cell_stage = BYTES_PER_CELL_STEP.get(integ, 128.0 * nstages) / nstages
     kern_ms = float(np.mean(stage_ms))
     achieved = cells_local * bytes_per_cell_stage / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
                 tj = json.load(f)
             if tj.get("block") == n and tj.get("blocks_per_gpu") == nb:
-                traffic = tj.get("dram_bytes_per_launch")
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
     fp64_peak = 18.27e12  # measured DFMA/DADD/DMUL issue rate, profiles/r01_fp64_microbench.txt
+    headline = args.flux == "Roe" and args.recon == "conservative"
+    fp64_per_cell = FP64_INSTR_PER_CELL_STAGE if headline else None
     out = {
         "metric": "cell-stage updates/sec", "value": value, "unit": "cell-stage updates/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -339,35 +521,49 @@ def run_ours(args):
         "config": {
             "workload": f"synthetic weak-scaling explosion: {nb}x{n_gpus} blocks of {n}x{n} cells, {args.flux} + Venkatakrishnan + GreenGauss, {args.recon} reconstruction, {integ}, CFL 0.7, reflection BCs" + ("" if args.ic == "explosion" else f", IC {args.ic}"),
             "blocks_per_gpu": nb, "block": n, "cells_total": cells_total, "stages_per_step": nstages,
-            "parallelism": f"block-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "parallelism": f"block-sharded x{n_gpus}: NCCL strip exchange per stage + dt all-reduce per step inside the captured step graph (pyh_comm_init)" if n_gpus > 1 else "single GPU",
             "l2_policy": f"inputs larger than L2 ({cells_local * 32 / 1e6:.0f} MB per state array per GPU vs 126 MB L2)",
+            "timed_call": "pyh_run (the device-resident loop Euler2D._solve drives): one CUDA graph per time step",
             "realizable_after_run": bool(ok),
+            "setup_s": {k_: round(v, 3) for k_, v in setup.items()},
         },
         "e2e": {
             "value": e2e_value, "unit": "cell-stage updates/s",
             "h2d_bytes_per_step": cells_total * 32, "d2h_bytes_per_step": cells_total * 32,
             "steps": e2e_steps,
-            "how": "per step: H2D of all block states from pinned host memory (pyh_upload_state_async + pyh_commit_uploads), ghost refresh, one time step, D2H of all block states into pinned host memory (pyh_download_state_async); steps are independent jobs pipelined over copy-in / compute / copy-out streams; wall clock from the first H2D to the last D2H, max over ranks",
+            "how": "per step: H2D of all block states from pinned host memory (pyh_upload_state_async + pyh_commit_uploads), ghost refresh, one time step (pyh_run), D2H of all block states into pinned host memory (pyh_download_state_async); steps are independent jobs pipelined over copy-in / compute / copy-out streams; wall clock from the first H2D to the last D2H, max over ranks",
         },
         "gpu_launches": launches_total,
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src, "kernel": "k_stage_march", "kernel_ms_avg": kern_ms,
             "algorithmic_bytes_per_cell_stage": bytes_per_cell_stage, "cells_per_launch": cells_local,
+            "binding_resource": "fp64_pipe",
             "fp64_pipe": {
-                "note": "bit-faithful fp64 (no FMA contraction): the FP64 pipe binds before HBM (DESIGN.md)",
+                "note": "what actually binds: bit-faithful fp64 (no FMA contraction, IEEE division / sqrt) needs ~1.1 k FP64 instructions per cell-stage, so the FP64 pipe saturates long before HBM (DESIGN.md section 4); `frac` above is the contract's HBM fraction, this is the pipe's",
                 "peak_issue_per_s": fp64_peak,
                 "cell_stage_per_s_kernel": cells_local / (kern_ms * 1e-3),
-                # FP64 instructions per cell-stage of the headline scheme, counted by ncu (profiles/r01n_summary.md);
-                # ncu (profiles/r01s_*): 1152 with the exact power-of-two scalings folded; the literal operation list of SURVEY.md section 8A needs 1187
-                "fp64_instr_per_cell_stage": 1152 if (args.flux == "Roe" and args.recon == "conservative") else None,
-                "frac": (1152 * cells_local / (kern_ms * 1e-3) / fp64_peak) if (args.flux == "Roe" and args.recon == "conservative") else None,
+                "fp64_instr_per_cell_stage": fp64_per_cell,
+                "frac": (fp64_per_cell * cells_local / (kern_ms * 1e-3) / fp64_peak) if fp64_per_cell else None,
             },
         },
     }
+    if sustained:
+        out["sustained"] = {"steps": sustained[1], "seconds": sus_ms * 1e-3, "value": cells_total * nstages * sustained[1] / (sus_ms * 1e-3),
+                            "unit": "cell-stage updates/s", "clocks": sustained[2]}
+    if selfcheck is not None:
+        out["selfcheck"] = selfcheck
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)   # the CPU arm may use every core again
+    if n_gpus == 1 and not args.no_named:
+        out["named_configs"] = {}
+        for name in NAMED:
+            try:
+                out["named_configs"][name] = run_named(torch, name, lrank, 0, peak)
+            except Exception as e:   # a missing fingerprint file must not take the headline line down
+                out["named_configs"][name] = {"error": repr(e)}
     if not args.no_cpu_baseline and n_gpus == 1:
         out["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_seconds)
     print(json.dumps(out), flush=True)
@@ -399,13 +595,15 @@ def _cpu_worker(rank, world, port, argd, seconds, steps, ret):
     from pyhype_b200.distributed import HaloExchanger, advance, distribute_blocks
 
     torch.set_num_threads(1)
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    nb, side = argd["blocks_per_gpu"], argd["cpu_block"]
-    blocks = ws_mesh(1, nb)
+    # under torch.distributed.run the parent's TORCHELASTIC_* / rendezvous variables would make this private gloo group
+    # connect as a CLIENT to a store nobody serves (TORCHELASTIC_USE_AGENT_STORE): drop them and rendezvous explicitly
+    for k in [k for k in os.environ if k.startswith("TORCHELASTIC_") or k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT")]:
+        del os.environ[k]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    nb, side, rows = argd["blocks_per_gpu"], argd["cpu_block"], argd["rows"]
+    blocks = ws_mesh(rows, nb)
     owner = distribute_blocks(len(blocks), world)
-    eng = OracleShardEngine(blocks, side, side, owner, rank, lambda x, y: ws_ic(x, y, BLOCK_LEN * nb, BLOCK_LEN),
+    eng = OracleShardEngine(blocks, side, side, owner, rank, lambda x, y: ws_ic(x, y, BLOCK_LEN * nb, BLOCK_LEN * rows),
                             flux=argd["flux"], limiter="Venkatakrishnan", recon="conservative",
                             integrator=argd["integrator"], CFL=0.7)
     hx = HaloExchanger(eng, owner, rank, backend_device=torch.device("cpu"))
@@ -439,7 +637,7 @@ def _cpu_worker(rank, world, port, argd, seconds, steps, ret):
     dist.destroy_process_group()
 
 
-def cpu_baseline(args, seconds=15.0, steps=None):
+def cpu_baseline(args, seconds=15.0, steps=None, rows=1):
     """Times the numpy port of the reference (oracle/, kind "port") on the host cores, on a bounded
     sample of the workload (same mesh / IC / scheme at reduced block size).  Like the reference under
     `mpiexec -n P` it runs one single-threaded process per block group (P = min(cores, blocks)),
@@ -450,20 +648,20 @@ def cpu_baseline(args, seconds=15.0, steps=None):
     import torch.multiprocessing as mp
 
     side, nb = args.cpu_block, args.blocks_per_gpu
-    nproc = max(1, min(os.cpu_count() or 1, nb, args.cpu_procs if args.cpu_procs > 0 else 1 << 30))
+    nproc = max(1, min(os.cpu_count() or 1, nb * rows, args.cpu_procs if args.cpu_procs > 0 else 1 << 30))
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
     sock.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    argd = dict(blocks_per_gpu=nb, cpu_block=side, flux=args.flux, integrator=args.integrator)
+    argd = dict(blocks_per_gpu=nb, cpu_block=side, flux=args.flux, integrator=args.integrator, rows=rows)
     mp.spawn(_cpu_worker, args=(nproc, port, argd, seconds, steps, ret), nprocs=nproc, join=True)
-    cells = nb * side * side
+    cells = nb * rows * side * side
     n, el, nstages = ret["steps"], ret["seconds"], ret["stages"]
     return {
         "value": cells * nstages * n / el, "unit": "cell-stage updates/s", "cores": nproc, "kind": "port",
-        "sample": f"{nb} blocks of {side}x{side} (same mesh/IC/scheme as the workload at reduced block size), {n} {args.integrator} steps, {el:.1f} s, {nproc} single-threaded processes (block-sharded like mpiexec -n {nproc}, ghost exchange + dt reduction over gloo)",
+        "sample": f"{nb}x{rows} blocks of {side}x{side} (same mesh/IC/scheme as the workload at reduced block size), {n} {args.integrator} steps, {el:.1f} s, {nproc} single-threaded processes (block-sharded like mpiexec -n {nproc}, ghost exchange + dt reduction over gloo)",
         "host_cores_available": os.cpu_count(),
     }
 
@@ -472,17 +670,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args, steps=args.steps)  # each worker does its own untimed warm-up step
+    rows = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))   # the N-GPU workload is an 8 x N grid of blocks
+    cb = cpu_baseline(args, steps=args.steps, rows=rows)  # each worker does its own untimed warm-up step
     nstages = 4 if args.integrator == "RK4" else len(__import__("oracle.muscl_oracle", fromlist=["TABLEAUX"]).TABLEAUX[args.integrator])
     side = args.cpu_block
-    cells = args.blocks_per_gpu * side * side
+    cells = args.blocks_per_gpu * rows * side * side
     out = {
         "impl": "reference", "metric": "cell-stage updates/sec", "value": cb["value"], "unit": "cell-stage updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": rows, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cells * nstages / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"synthetic weak-scaling explosion: {args.blocks_per_gpu}x1 blocks, {args.flux} + Venkatakrishnan + GreenGauss, conservative reconstruction, {args.integrator}, CFL 0.7, reflection BCs; CPU arm runs a bounded sample at {side}x{side} cells per block",
+            "workload": f"synthetic weak-scaling explosion: {args.blocks_per_gpu}x{rows} blocks, {args.flux} + Venkatakrishnan + GreenGauss, conservative reconstruction, {args.integrator}, CFL 0.7, reflection BCs; CPU arm runs a bounded sample at {side}x{side} cells per block",
             "blocks_per_gpu": args.blocks_per_gpu, "block": side,
         },
         "cpu_baseline": cb,
@@ -509,7 +708,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = min(cores, blocks))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="ws", choices=["ws", "explosion_multi", "dmr"],
+                    help="ws: the weak-scaling workload the metric is quoted on (default); explosion_multi / dmr: the reference's own configurations at their named sizes as the main line (1 GPU)")
+    ap.add_argument("--no-named", action="store_true", help="skip the named-configuration sub-lines of the default N=1 run")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the sharded == single-GPU bit check at the start of an N>1 run")
+    ap.add_argument("--sustain-steps", type=int, default=300, help="second, long timed window (0 = off)")
     args = ap.parse_args()
+    args.steps_given = any(a == "--steps" or a.startswith("--steps=") for a in sys.argv[1:])
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -109,6 +109,12 @@ int pyh_download_state(void* ctx, int gid, double* aos);
  * state that the setter broadcasts over the block, states/base.py:99-107): every interior cell of block gid is
  * set to the conservative 4-vector `state`. */
 int pyh_fill_uniform(void* ctx, int gid, const double* state);
+/* Two-state initial conditions without an upload (examples/explosion_multi/initial_condition.py:53-59,
+ * examples/dmr/initial_condition.py:55-58: np.where over a condition on the cell centroids block.mesh.x / .y): every interior
+ * cell whose centroid lies in the closed box [x0, x1] x [y0, y1] (bounds may be +-inf) is set to the conservative 4-vector
+ * `inside`, every other cell to `outside` -- or left untouched when outside == NULL.  The centroids are the device's
+ * bit-identical copy of QuadMesh.x / .y (pyhype/mesh/quad_mesh.py:172-184), so the result equals the uploaded numpy fill. */
+int pyh_fill_box(void* ctx, int gid, double x0, double x1, double y0, double y1, const double* inside, const double* outside);
 /* Asynchronous variants for streaming use (replaces nothing in the reference, which keeps state on the
  * host; serves Solver.write_solution, pyhype/solvers/base.py:158-172, without stalling the time loop,
  * and back-to-back independent runs).  Host buffers should be page-locked; they are read / written
@@ -178,10 +184,28 @@ int pyh_stage_overlapped(void* ctx, int stage);
 int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream);
 int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas);
 
+/* Multi-rank transport owned by the library: NCCL over NVLink, one context (= one GPU) per rank.  Replaces the
+ * mpi4py calls of the reference: Isend / Irecv per ghost strip (pyhype/blocks/ghost.py:169-241), the Waitall of
+ * Blocks.apply_boundary_condition (pyhype/blocks/base.py:454-465) and the gather + bcast of the time step
+ * (pyhype/solvers/base.py:128-131).  libnccl.so.2 is bound at run time (dlopen; PYH_NCCL_LIB overrides the name).
+ *   pyh_comm_unique_id : rank 0 creates the 128-byte NCCL id; the host distributes it (any side channel).
+ *   pyh_comm_init      : collective over all ranks, after pyh_finalize.  owner[g] = rank that owns global block g
+ *                        (Blocks.distribute_blocks_to_processes, pyhype/blocks/base.py:473-513).
+ * Once initialised, pyh_apply_bc, pyh_step, pyh_run, pyh_local_dt, pyh_get_dt and pyh_realizable are COLLECTIVE:
+ * every rank must call them in the same order.  Each ghost refresh packs the edge strips remote neighbours need,
+ * exchanges them in ONE grouped ncclSend / ncclRecv batch and unpacks them, on the context's stream; the CFL minimum
+ * and the realizability flag are reduced by one 16-byte ncclAllReduce(min).  A rank may own no blocks. */
+#define PYH_COMM_ID_BYTES 128
+int pyh_comm_unique_id(void* id_out);
+int pyh_comm_init(void* ctx, int32_t rank, int32_t world, const void* id, const int32_t* owner, int32_t nblocks_total);
+int pyh_comm_info(void* ctx, int32_t* rank, int32_t* world, int32_t* n_msgs, int64_t* doubles_per_exchange);
+
 /* Euler2D._solve loop (pyhype/solvers/Euler2D.py:195-210), device resident: dt, t and the step
  * counter stay on the GPU; the host only polls every `poll_every` steps.  dts_out (may be NULL)
  * receives up to dts_cap per-step dt values.  *unrealizable is set when rho<=0 or e<=0 was seen
- * (Euler2D._realizability_check, Euler2D.py:144-152). Single-rank contexts only. */
+ * (Euler2D._realizability_check, Euler2D.py:144-152).  One time step (CFL reduction, [dt allreduce,]
+ * stages, [strip exchange,] ghost refresh) is captured once as a CUDA graph and replayed.  Contexts with
+ * remote neighbours need pyh_comm_init first; the call is then collective. */
 int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32_t poll_every,
             int64_t* steps_done, int32_t* unrealizable, double* dts_out, int64_t dts_cap);
 

@@ -42,6 +42,23 @@ CASES = {
                 cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive",
                          t_final=0.25),
                 what="examples/dmr scheme at BASELINE.json's 500x500 blocks (shipped: 50x50), first 40 steps"),
+    # BASELINE.json configs[2]: examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall,
+    # 15 degree ramp), with the shipped flux (HLLL) and with the one BASELINE.json names (Roe); first 50 steps
+    "wedge": dict(mesh="wedge_mesh", mesh_args=(60,), ic="wedge_ic", nx=60, ny=60, stride=6, checkpoints=[10, 50],
+                  cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.3, reconstruction_type="primitive", t_final=20.0),
+                  what="examples/supersonic_wedge as shipped (HLLL, primitive reconstruction, RK2, CFL 0.3), first 50 steps"),
+    "wedge_roe": dict(mesh="wedge_mesh", mesh_args=(60,), ic="wedge_ic", nx=60, ny=60, stride=6, checkpoints=[10, 50],
+                      cfg=dict(fvm_flux_function_type="Roe", time_integrator="RK2", CFL=0.3, reconstruction_type="primitive", t_final=20.0),
+                      what="examples/supersonic_wedge with the Roe flux BASELINE.json names, first 50 steps"),
+    # BASELINE.json configs[3]: examples/jet at its shipped size (9 stacked blocks of 1080 x 60), shipped flux (HLLL) and the
+    # HLLE that BASELINE.json names (runs only in the two-edit patched reference); first 50 steps
+    "jet": dict(mesh="jet_mesh", mesh_args=(60,), ic="jet_ic", nx=1080, ny=60, stride=12, checkpoints=[10, 50],
+                cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive", t_final=25.0),
+                what="examples/jet as shipped (HLLL, primitive reconstruction, RK2, CFL 0.4), first 50 steps"),
+    "jet_hlle": dict(mesh="jet_mesh", mesh_args=(60,), ic="jet_ic", nx=1080, ny=60, stride=12, checkpoints=[5, 10, 16], patch_hlle=True, aborts_next=True,
+                     cfg=dict(fvm_flux_function_type="HLLE", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive", t_final=25.0),
+                     what="examples/jet with the HLLE flux BASELINE.json names: two-edit PATCHED reference (oracle/refharness.patch_hlle); the reference's own "
+                          "run stops with an unrealizable state in step 17 (inlet start-up), so the fingerprint holds steps 5, 10, 16 and the abort"),
 }
 
 
@@ -54,7 +71,10 @@ def main(name):
     from make_golden import ref_blocks
 
     c = CASES[name]
-    blocks = getattr(cases, c["mesh"])()
+    if c.get("patch_hlle"):
+        rh.activate()
+        rh.patch_hlle()
+    blocks = getattr(cases, c["mesh"])(*c.get("mesh_args", ()))
     ic = getattr(cases, c["ic"])
 
     class IC:
@@ -64,11 +84,11 @@ def main(name):
     config = rh.make_config(nx=c["nx"], ny=c["ny"], initial_condition=IC(), **c["cfg"])
     run = rh.RefRun(config, ref_blocks(blocks))
     t_final = float(run.solver.t_final)
-    out, meta = {}, dict(name=name, what=c["what"], nx=c["nx"], ny=c["ny"], stride=c["stride"], mesh=c["mesh"], ic=c["ic"],
+    out, meta = {}, dict(name=name, what=c["what"], nx=c["nx"], ny=c["ny"], stride=c["stride"], mesh=c["mesh"], mesh_args=list(c.get("mesh_args", ())), ic=c["ic"],
                          flux=config.fvm_flux_function_type, limiter=config.fvm_slope_limiter_type,
                          recon=c["cfg"].get("reconstruction_type", "conservative"), integrator=config.time_integrator,
                          CFL=config.CFL, t_final_nd=t_final, gids=sorted(blocks), checkpoints=[], digests={}, raw_sha16={},
-                         generator="oracle/make_named_fingerprints.py on the unmodified reference")
+                         generator="oracle/make_named_fingerprints.py on the unmodified reference" + (" + HLLE 2-edit patch" if c.get("patch_hlle") else ""))
     t0 = time.time()
     for cp in c["checkpoints"]:
         target = 10**9 if cp < 0 else cp
@@ -85,6 +105,16 @@ def main(name):
             sums.append(U.sum(axis=(0, 1)))
         out[f"sums_{n}"] = np.array(sums)
         print(f"[{name}] step {n}  t = {run.solver.t:.6f} / {t_final:.6f}  ({time.time() - t0:.0f} s)", flush=True)
+    if c.get("aborts_next"):
+        # the reference's realizability check (Euler2D.py:144-152) must stop the run in the next step
+        t_before = float(run.solver.t)
+        try:
+            run.step(1)
+            raise RuntimeError("expected the reference to abort in the next step")
+        except SystemExit:
+            meta["aborts_in_step"] = n + 1
+        run.dts = run.dts[:n]
+        run.solver.t = t_before
     meta["t_end"] = float(run.solver.t)
     meta["reached_t_final"] = not (run.solver.t < t_final)
     out["dts"] = np.array(run.dts)

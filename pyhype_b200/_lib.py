@@ -65,6 +65,7 @@ SIGNATURES = {
     "pyh_upload_state": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_download_state": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_fill_uniform": (C.c_int, [_vp, C.c_int, c_double_p]),
+    "pyh_fill_box": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p, c_double_p]),
     "pyh_upload_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_commit_uploads": (C.c_int, [_vp]),
     "pyh_download_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
@@ -97,6 +98,9 @@ SIGNATURES = {
          c_double_p, C.c_int64],
     ),
     "pyh_realizable": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "pyh_comm_unique_id": (C.c_int, [_vp]),
+    "pyh_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.POINTER(C.c_int32), C.c_int32]),
+    "pyh_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pyh_residual": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_debug_fetch": (C.c_int, [_vp, C.c_int, C.c_int, c_double_p]),
     "pyh_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),

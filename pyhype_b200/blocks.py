@@ -25,12 +25,36 @@ class DeviceBackedState(ConservativeState):
         self._device_newer = False
         self._host_touched = True
         self._uniform = None   # pending (4,) state assigned as a (1, 1, 4) array: filled on the device, no upload
+        self._boxes = []       # pending two-state fills (fill_box) on top of it, in order; also evaluated on the device
         super().__init__(fluid=fluid, shape=shape)
 
     def _materialize_uniform(self):
         if self._uniform is not None:
             self._data[:, :, :] = self._uniform.reshape(1, 1, 4)   # the reference's broadcast (states/base.py:99-107)
             self._uniform = None
+        if self._boxes:
+            x, y = self._sync.centroids()
+            for x0, x1, y0, y1, inside, outside in self._boxes:   # the reference's np.where over the centroids
+                cond = np.logical_and(np.logical_and(x >= x0, x <= x1), np.logical_and(y >= y0, y <= y1))
+                self._data[:, :, :] = np.where(cond, inside.reshape(1, 1, 4), self._data if outside is None else outside.reshape(1, 1, 4))
+            self._boxes = []
+
+    def fill_box(self, x0, x1, y0, y1, inside, outside=None):
+        """Two-state fill over the cell centroids, the pattern of the reference's explosion / implosion / dmr initial
+        conditions (``np.where(cond(block.mesh.x, block.mesh.y), left_state.data, right_state.data)``,
+        examples/explosion_multi/initial_condition.py:53-59): cells with x0 <= x <= x1 and y0 <= y <= y1 get ``inside``
+        (a 4-vector or (1, 1, 4) array), the others ``outside`` (None: keep).  Kept as 2 x 4 numbers and evaluated by a fill
+        kernel on the device's bit-identical centroids -- no (ny, nx, 4) array is built or uploaded unless host code reads
+        ``data``.  ``make_non_dimensional`` acts on the pending numbers."""
+        if self._device_newer:
+            self.data  # pull the device copy first: the fill applies on top of it
+        inside = np.array(inside, dtype=np.float64).reshape(4)
+        outside = None if outside is None else np.array(outside, dtype=np.float64).reshape(4)
+        if outside is not None:
+            self._uniform, self._boxes = None, []   # the whole block is redefined
+        self._boxes.append((float(x0), float(x1), float(y0), float(y1), inside, outside))
+        self._host_touched = True
+        self.cache.clear()
 
     @property
     def data(self):
@@ -64,21 +88,35 @@ class DeviceBackedState(ConservativeState):
             self._data[:, :, :] = array
         self.cache.clear()
 
+    def _pending_defines_block(self):
+        """True when the pending fills alone determine every cell (uniform flood, or a box fill with an outside state)."""
+        return self._uniform is not None or (bool(self._boxes) and self._boxes[0][5] is not None)
+
     def make_non_dimensional(self):
-        if self._uniform is not None and not self._device_newer:
+        if self._pending_defines_block() and not self._device_newer:
             ff = self.fluid.far_field   # same divisions, on the 4 numbers instead of every cell (states/base.py:93-97)
-            self._uniform[0] /= ff.rho
-            self._uniform[1] /= ff.rho * ff.a
-            self._uniform[2] /= ff.rho * ff.a
-            self._uniform[3] /= ff.rho * ff.a**2
+            vecs = ([self._uniform] if self._uniform is not None else []) + [v for b in self._boxes for v in (b[4], b[5]) if v is not None]
+            for v in vecs:
+                v[0] /= ff.rho
+                v[1] /= ff.rho * ff.a
+                v[2] /= ff.rho * ff.a
+                v[3] /= ff.rho * ff.a**2
             return
+        self.data   # materialise pending fills on the host, then the reference's elementwise division
         super().make_non_dimensional()
 
     def push_if_touched(self):
         if self._host_touched and not self._device_newer:
-            if self._uniform is not None:
-                self._sync.fill_uniform(self._uniform)
+            if self._pending_defines_block():
+                if self._uniform is not None:
+                    self._sync.fill_uniform(self._uniform)
+                for x0, x1, y0, y1, inside, outside in self._boxes:
+                    self._sync.fill_box(x0, x1, y0, y1, inside, outside)
+                # the host copy is now stale; it is re-created (download) on the next read of .data
+                self._uniform, self._boxes = None, []
+                self._device_newer = True
             else:
+                self._materialize_uniform()
                 self._sync.upload(np.ascontiguousarray(self._data, dtype=np.float64))
         self._host_touched = False
 
@@ -88,8 +126,8 @@ class DeviceBackedState(ConservativeState):
 
 
 class _Sync:
-    def __init__(self, engine, gid):
-        self.engine, self.gid = engine, gid
+    def __init__(self, engine, gid, mesh=None):
+        self.engine, self.gid, self.mesh = engine, gid, mesh
 
     def upload(self, arr):
         self.engine.upload(self.gid, arr)
@@ -99,6 +137,12 @@ class _Sync:
 
     def fill_uniform(self, state):
         self.engine.fill_uniform(self.gid, state)
+
+    def fill_box(self, x0, x1, y0, y1, inside, outside):
+        self.engine.fill_box(self.gid, x0, x1, y0, y1, inside, outside)
+
+    def centroids(self):
+        return self.mesh.x, self.mesh.y
 
 
 class _GhostView:
@@ -115,7 +159,6 @@ class _GhostView:
         @property
         def data(self):
             self._block._solver._flush_host_states()
-            self._block._solver._wait_halo()   # an overlapped remote exchange may still be in flight
             return self._block._engine.download_ghost(self._block.global_block_num, self._side)
 
     def __init__(self, block):
@@ -147,7 +190,7 @@ class QuadBlock:
 
     def _attach(self, engine):
         self._engine = engine
-        self.state = DeviceBackedState(self.config.fluid, (self.mesh.ny, self.mesh.nx, 4), _Sync(engine, self.global_block_num))
+        self.state = DeviceBackedState(self.config.fluid, (self.mesh.ny, self.mesh.nx, 4), _Sync(engine, self.global_block_num, self.mesh))
 
     @property
     def reconstruction_type(self):

@@ -1,5 +1,6 @@
 // pyh_api.cu -- context, memory management and the extern "C" entry points of include/pyh_b200.h
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include "pyh_kernels.cuh"
 #include "pyh_march_tu.cuh"
 #include "pyh_plan.cuh"
+#include "pyh_comm.cuh"
 
 using namespace pyh;
 
@@ -23,6 +25,13 @@ static int set_err(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+#define NC(call)                                                                                     \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != 0)                                                                                 \
+            return set_err(PYH_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                           nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "NCCL error"); \
+    } while (0)
 #define CU(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -88,9 +97,11 @@ struct Ctx {
     // captured once as a CUDA graph and replayed
     cudaGraphExec_t run_graph = nullptr;
     int run_graph_steps = 0;
+    int run_graph_i0 = 0;          // buffer holding the solution when the captured period starts
     long long run_graph_launches = 0;
     unsigned long long halo_epoch_issued = 0;   // stamp handed to the latest pyh_unpack_halo_on
     int n_remote_ctas = 0;
+    Comm comm;                                  // multi-rank transport (pyh_comm_init); comm.comm == nullptr: single rank
 };
 
 int ensure_streaming(Ctx* c) {
@@ -166,6 +177,7 @@ void choose_march_shape(Ctx* c) {
 }
 
 int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, bool overlapped = false) {
+    if (c->blocks.empty()) return 0;   // a rank without blocks only takes part in the reductions (blocks/base.py:473-513 allows it)
     const int nq = c->cfg.num_quadrature_points;
     MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon, nq);
     const int nt = c->march_nt, tys = c->march_tys;
@@ -199,6 +211,7 @@ StagePlan make_plan(Ctx* c, int s, int cur, int next) {
 }
 
 int do_ghost(Ctx* c, int buf) {
+    if (c->blocks.empty()) return 0;
     int m = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(m, 128), 4, (unsigned)c->blocks.size());
     k_ghost<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po, c->po.H[buf], c->d_ctl);
@@ -228,10 +241,43 @@ int set_active(Ctx* c, int active) {
 }
 
 int launch_dt(Ctx* c, int buf, int respect_active = 0) {
+    if (c->blocks.empty()) return 0;   // dtmin_bits stays +inf: Solver.get_dt's np.inf for a rank without blocks
     dim3 grid(cdiv(c->lay.nx, 256), cdiv(c->lay.ny, DT_ROWS), (unsigned)c->blocks.size());
     k_dt<<<grid, 256, 0, c->stream>>>(c->d_blks, c->lay, c->po, c->po.H[buf], (int)c->blocks.size(), c->d_ctl, c->C, respect_active);
     CU(cudaGetLastError());
     c->launches++;
+    return 0;
+}
+
+// Remote ghost strips of buffer `buf` (GhostBlock.send_boundary_data / recieve_boundary_data / apply_recv_buffers_to_state,
+// blocks/ghost.py:169-241, and the Waitall of blocks/base.py:454-465): pack the edge strips the neighbour ranks need, ONE
+// grouped ncclSend / ncclRecv batch, unpack into the ghost frames -- all in order on the compute stream (capturable).
+int exchange_halo(Ctx* c, int buf) {
+    Comm& m = c->comm;
+    if (!m.comm || c->slots.empty()) return 0;
+    NcclApi& N = nccl_api();
+    const int mx = std::max(c->lay.nx, c->lay.ny);
+    dim3 grid(cdiv(mx, 128), (unsigned)c->slots.size());
+    k_pack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_send);
+    CU(cudaGetLastError());
+    NC(N.GroupStart());
+    for (const HaloMsg& r : m.recvs) NC(N.Recv(m.d_recv + r.offset, (size_t)r.len, kNcclFloat64, r.peer, m.comm, c->stream));
+    for (const HaloMsg& q : m.sends) NC(N.Send(m.d_send + q.offset, (size_t)q.len, kNcclFloat64, q.peer, m.comm, c->stream));
+    NC(N.GroupEnd());
+    k_unpack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_recv);
+    CU(cudaGetLastError());
+    c->launches += 2;
+    return 0;
+}
+
+// Global CFL minimum and realizability flag (Solver.get_dt gathers and broadcasts the minimum, solvers/base.py:128-131;
+// min is exact, so the result does not depend on the rank count): one in-place ncclAllReduce(min) over the two adjacent
+// 64-bit words {dtmin_bits, allok} of the device control block.
+int reduce_dt(Ctx* c) {
+    Comm& m = c->comm;
+    if (!m.comm) return 0;
+    static_assert(offsetof(Control, allok) == offsetof(Control, dtmin_bits) + sizeof(unsigned long long), "dtmin_bits and allok must be adjacent");
+    NC(nccl_api().AllReduce(&c->d_ctl->dtmin_bits, &c->d_ctl->dtmin_bits, 2, kNcclUint64, kNcclMin, m.comm, c->stream));
     return 0;
 }
 
@@ -289,6 +335,7 @@ int pyh_create(const pyh_config* cfg, void** out) {
     Control h;
     memset(&h, 0, sizeof(h));
     h.dtmin_bits = DKEY_INF;
+    h.allok = 1ull;
     h.active = 1;
     CU(cudaMemcpy(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tmp, 64 * sizeof(double)));
@@ -339,7 +386,7 @@ int pyh_add_block(void* ctx, const pyh_block_desc* b) {
     if ((rc = put(b->sin_h, sh, ny + 1, nx))) return rc;
     CU(cudaMemcpyAsync(c->d_scratch, b->nodes_x, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_scratch + nn, b->nodes_y, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy, c->cfg.num_quadrature_points, c->C);
+    k_geometry<<<cdiv(nn, 256), 256, 0, c->stream>>>(L, c->d_scratch, c->d_scratch + nn, dxy, Lv, Lh, cdx, cdy, slab + po.xc, slab + po.yc, c->cfg.num_quadrature_points, c->C);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     D.dbg = nullptr;
@@ -385,7 +432,6 @@ int pyh_finalize(void* ctx) {
     Ctx* c = as_ctx(ctx);
     if (!c) return set_err(PYH_ERR_INVALID, "null context");
     if (c->finalized) return set_err(PYH_ERR_STATE, "pyh_finalize called twice");
-    if (c->blocks.empty()) return set_err(PYH_ERR_STATE, "no blocks");
     CU(cudaSetDevice(c->cfg.device));
     // halo slots in (gid, side) ascending order
     std::vector<std::pair<int, int>> order;
@@ -417,8 +463,8 @@ int pyh_finalize(void* ctx) {
     }
     std::vector<BlkDev> tmp;
     for (auto& hb : c->blocks) tmp.push_back(hb.dev);
-    CU(cudaMalloc(&c->d_blks, tmp.size() * sizeof(BlkDev)));
-    CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_blks, std::max<size_t>(tmp.size(), 1) * sizeof(BlkDev)));
+    if (!tmp.empty()) CU(cudaMemcpy(c->d_blks, tmp.data(), tmp.size() * sizeof(BlkDev), cudaMemcpyHostToDevice));
     if (!c->slots.empty()) {
         CU(cudaMalloc(&c->d_slots, c->slots.size() * sizeof(HaloSlot)));
         CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
@@ -467,6 +513,9 @@ int pyh_destroy(void* ctx) {
     if (c->ev_out_ready) cudaEventDestroy(c->ev_out_ready);
     for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
     if (c->run_graph) cudaGraphExecDestroy(c->run_graph);
+    if (c->comm.comm) nccl_api().CommDestroy(c->comm.comm);
+    if (c->comm.d_send) cudaFree(c->comm.d_send);
+    if (c->comm.d_recv) cudaFree(c->comm.d_recv);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -517,6 +566,20 @@ int pyh_fill_uniform(void* ctx, int gid, const double* state) {
     if (!state) return set_err(PYH_ERR_INVALID, "null state pointer");
     size_t n = (size_t)c->lay.nx * c->lay.ny;
     k_fill_uniform<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], state[0], state[1], state[2], state[3]);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pyh_fill_box(void* ctx, int gid, double x0, double x1, double y0, double y1, const double* inside, const double* outside) {
+    Ctx* c = as_ctx(ctx);
+    GET_BLOCK(c, gid, hb);
+    if (!inside) return set_err(PYH_ERR_INVALID, "null state pointer");
+    size_t n = (size_t)c->lay.nx * c->lay.ny;
+    const double z[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* o = outside ? outside : z;
+    k_fill_box<<<cdiv(n, 256), 256, 0, c->stream>>>(c->lay, hb.dev.base + c->po.H[c->i0], hb.dev.base + c->po.xc, hb.dev.base + c->po.yc,
+                                                    x0, x1, y0, y1, inside[0], inside[1], inside[2], inside[3], outside ? 1 : 0, o[0], o[1], o[2], o[3]);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -630,6 +693,7 @@ int pyh_apply_bc(void* ctx) {
     CU(cudaSetDevice(c->cfg.device));
     int rc = set_active(c, 1);
     if (rc) return rc;
+    if ((rc = exchange_halo(c, c->cur))) return rc;   // no-op without pyh_comm_init (host-driven transport: pyh_pack_halo & co)
     return do_ghost(c, c->cur);
 }
 
@@ -686,6 +750,7 @@ int pyh_local_dt(void* ctx, double* dev_dt_out) {
     CU(cudaSetDevice(c->cfg.device));
     int rc = launch_dt(c, c->i0);
     if (rc) return rc;
+    if ((rc = reduce_dt(c))) return rc;   // with pyh_comm_init: the GLOBAL minimum
     k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, dev_dt_out);
     CU(cudaGetLastError());
     c->launches++;
@@ -776,11 +841,13 @@ int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas) {
 
 int pyh_step(void* ctx, double dt) {
     Ctx* c = as_ctx(ctx);
-    if (c && !c->slots.empty()) return set_err(PYH_ERR_STATE, "pyh_step on a context with remote neighbours; drive the stages from the host");
+    if (c && !c->slots.empty() && !c->comm.comm)
+        return set_err(PYH_ERR_STATE, "pyh_step on a context with remote neighbours and no pyh_comm_init; drive the stages from the host");
     int rc = pyh_step_begin(ctx, dt);
     if (rc) return rc;
     for (int s = 0; s < c->cfg.num_stages; ++s) {
         if ((rc = do_stage(c, s))) return rc;
+        if ((rc = exchange_halo(c, c->cur))) return rc;
         if ((rc = do_ghost(c, c->cur))) return rc;
     }
     c->stage_next = c->cfg.num_stages;
@@ -792,7 +859,8 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     Ctx* c = as_ctx(ctx);
     if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
     if (!t_inout) return set_err(PYH_ERR_INVALID, "null pointer");
-    if (!c->slots.empty()) return set_err(PYH_ERR_STATE, "pyh_run needs all neighbours local (single-rank context)");
+    if (!c->slots.empty() && !c->comm.comm)
+        return set_err(PYH_ERR_STATE, "pyh_run on a context with remote neighbours needs pyh_comm_init (or drive the stages from the host)");
     CU(cudaSetDevice(c->cfg.device));
     if (poll_every < 1) poll_every = 64;
     if (max_steps < 0) max_steps = (int64_t)1 << 62;
@@ -806,7 +874,7 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     }
     Control h;
     memset(&h, 0, sizeof(h));
-    h.t = *t_inout; h.t_final = t_final; h.dtmin_bits = DKEY_INF; h.active = 1; h.nsteps = 0; h.bad = 0;
+    h.t = *t_inout; h.t_final = t_final; h.dtmin_bits = DKEY_INF; h.allok = 1ull; h.active = 1; h.nsteps = 0; h.bad = 0;
     double* ddts = (dts_out && dts_cap > 0) ? c->d_dts : nullptr;
     h.dts = ddts; h.dts_cap = ddts ? dts_cap : 0;
     CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
@@ -815,10 +883,12 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     auto enqueue_step = [&]() -> int {
         int r;
         if ((r = launch_dt(c, c->i0, 1))) return r;
+        if ((r = reduce_dt(c))) return r;
         k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 0, nullptr);
         CU(cudaGetLastError());
         for (int s = 0; s < c->cfg.num_stages; ++s) {
             if ((r = do_stage(c, s))) return r;
+            if ((r = exchange_halo(c, c->cur))) return r;
             if ((r = do_ghost(c, c->cur))) return r;
         }
         k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl);
@@ -827,12 +897,14 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         return 0;
     };
     static const bool no_graph = getenv("PYH_NO_GRAPH") != nullptr;
+    int64_t enqueued = 0;          // steps handed to the stream in this call (>= steps the device executes)
     const int period = (c->cfg.num_stages == 1) ? 2 : 1;   // steps after which the buffer roles repeat
     if (!no_graph && !c->run_graph && max_steps >= 2 * period) {
         // first steps run eagerly (also configures the kernels' attributes), then one period is captured
         for (int n = 0; n < period; ++n) if ((rc = enqueue_step())) return rc;
         const long long l0 = c->launches;
         cudaGraph_t g = nullptr;
+        c->run_graph_i0 = c->i0;
         CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         for (int n = 0; n < period; ++n) {
             if ((rc = enqueue_step())) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); return rc; }
@@ -845,6 +917,7 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         if (e != cudaSuccess) return set_err(PYH_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         c->run_graph_steps = period;
         max_steps -= period;   // the eager steps count
+        enqueued += period;
         if (steps_done) *steps_done = 0;
     }
     int64_t issued = 0;
@@ -852,6 +925,9 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         int64_t chunk = std::min<int64_t>(poll_every, max_steps - issued);
         int64_t n = 0;
         if (c->run_graph && !no_graph) {
+            // the captured period has the buffer roles of its first step baked in: realign with one eager step if an odd
+            // number of single-stage steps has been taken since (ExplicitEuler1 only; roles of longer tableaux repeat every step)
+            if (c->i0 != c->run_graph_i0 && n < chunk) { if ((rc = enqueue_step())) return rc; ++n; }
             for (; n + c->run_graph_steps <= chunk; n += c->run_graph_steps) {
                 CU(cudaGraphLaunch(c->run_graph, c->stream));
                 c->launches += c->run_graph_launches;
@@ -859,12 +935,22 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         }
         for (; n < chunk; ++n) if ((rc = enqueue_step())) return rc;
         issued += chunk;
+        enqueued += chunk;
         CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (!h.active || h.bad || !(h.t < h.t_final)) break;
     }
+    if (c->cfg.num_stages == 1) {
+        // Single-stage tableaux alternate two buffers and the host flipped their roles once per ENQUEUED step, but the device
+        // executed only the first h.nsteps of them (the rest early-exit once t >= t_final or the state went bad): the buffer
+        // the device wrote last is the authoritative solution.
+        CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if ((enqueued - (int64_t)h.nsteps) & 1) { std::swap(c->i0, c->i1); c->cur = c->i0; }
+    }
     // final realizability check of the last state (Euler2D.py:204)
     if ((rc = launch_dt(c, c->i0))) return rc;
+    if ((rc = reduce_dt(c))) return rc;
     k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, c->d_tmp);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -889,6 +975,7 @@ int pyh_realizable(void* ctx, int32_t* ok_out) {
     CU(cudaMemcpyAsync(&c->d_ctl->bad, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     int rc = launch_dt(c, c->i0);
     if (rc) return rc;
+    if ((rc = reduce_dt(c))) return rc;
     k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, c->d_tmp);
     CU(cudaGetLastError());
     int bad = 0;
@@ -967,6 +1054,64 @@ int pyh_debug_fetch(void* ctx, int gid, int what, double* aos_out) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(aos_out, c->d_scratch, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pyh_comm_unique_id(void* id_out) {
+    if (!id_out) return set_err(PYH_ERR_INVALID, "null pointer");
+    NcclApi& N = nccl_api();
+    if (N.error) return set_err(PYH_ERR_STATE, "NCCL unavailable: %s", N.error);
+    NcclUniqueId id;
+    NC(N.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+int pyh_comm_init(void* ctx, int32_t rank, int32_t world, const void* id, const int32_t* owner, int32_t nblocks_total) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (!id || !owner || world < 1 || rank < 0 || rank >= world) return set_err(PYH_ERR_INVALID, "bad rank / world / null pointer");
+    if (c->comm.comm) return set_err(PYH_ERR_STATE, "pyh_comm_init called twice");
+    NcclApi& N = nccl_api();
+    if (N.error) return set_err(PYH_ERR_STATE, "NCCL unavailable: %s", N.error);
+    CU(cudaSetDevice(c->cfg.device));
+    Comm& m = c->comm;
+    m.rank = rank; m.world = world;
+    // message lists: the strip this rank sends for slot (gid, side) is named (gid, side); the strip it receives for that slot
+    // is the neighbour's (nbr_gid, opposite side) -- the same ordering rule as pyhype_b200/distributed.py:exchange_plan
+    static const int opposite[4] = {PYH_WEST, PYH_EAST, PYH_SOUTH, PYH_NORTH};
+    for (size_t i = 0; i < c->slots.size(); ++i) {
+        const HaloSlot& hs = c->slots[i];
+        const int ng = c->slot_nbr_gid[i];
+        if (ng < 0 || ng >= nblocks_total) return set_err(PYH_ERR_INVALID, "neighbour block %d outside the owner table (%d blocks)", ng, nblocks_total);
+        const int peer = owner[ng];
+        if (peer < 0 || peer >= world || peer == rank) return set_err(PYH_ERR_INVALID, "block %d: remote neighbour %d is owned by rank %d", c->blocks[hs.blk].d.gid, ng, peer);
+        const long long len = 4LL * ((hs.side == PYH_EAST || hs.side == PYH_WEST) ? c->lay.ny : c->lay.nx);
+        m.sends.push_back(HaloMsg{peer, c->blocks[hs.blk].d.gid, hs.side, hs.offset, len});
+        m.recvs.push_back(HaloMsg{peer, ng, opposite[hs.side], hs.offset, len});
+    }
+    std::sort(m.sends.begin(), m.sends.end(), msg_less);
+    std::sort(m.recvs.begin(), m.recvs.end(), msg_less);
+    m.doubles = c->halo_doubles;
+    if (m.doubles > 0) {
+        CU(cudaMalloc(&m.d_send, (size_t)m.doubles * sizeof(double)));
+        CU(cudaMalloc(&m.d_recv, (size_t)m.doubles * sizeof(double)));
+    }
+    NcclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NC(N.CommInitRank(&m.comm, world, uid, rank));
+    // the cached single-rank graph (if any) does not contain the exchange
+    if (c->run_graph) { cudaGraphExecDestroy(c->run_graph); c->run_graph = nullptr; }
+    return 0;
+}
+
+int pyh_comm_info(void* ctx, int32_t* rank, int32_t* world, int32_t* n_msgs, int64_t* doubles_per_exchange) {
+    Ctx* c = as_ctx(ctx);
+    if (!c) return set_err(PYH_ERR_INVALID, "null context");
+    if (rank) *rank = c->comm.comm ? c->comm.rank : 0;
+    if (world) *world = c->comm.comm ? c->comm.world : 1;
+    if (n_msgs) *n_msgs = (int32_t)c->comm.sends.size();
+    if (doubles_per_exchange) *doubles_per_exchange = c->comm.doubles;
     return 0;
 }
 

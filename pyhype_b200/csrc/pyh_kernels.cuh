@@ -171,7 +171,7 @@ k_dt(const BlkDev* __restrict__ blks, Layout lay, PlaneOffsets po, unsigned buf,
         }
         if (l == 0) {
             atomicMin(&ctl->dtmin_bits, dkey(m));
-            if (bad) atomicOr(&ctl->bad, 1);
+            if (bad) { atomicOr(&ctl->bad, 1); atomicExch(&ctl->allok, 0ull); }
         }
     }
 }
@@ -179,8 +179,10 @@ k_dt(const BlkDev* __restrict__ blks, Layout lay, PlaneOffsets po, unsigned buf,
 // mode 0: device-resident loop (Solver.get_dt clamp + while t < t_final)
 // mode 1: write CFL*min to *out only (pyh_local_dt / pyh_get_dt)
 __global__ void k_dt_finalize(Control* ctl, double cfl, Tableau tab, int mode, double* out) {
-    double dt = cfl * dunkey(ctl->dtmin_bits);      // quad_block.py:436 ; min over blocks is exact
+    double dt = cfl * dunkey(ctl->dtmin_bits);      // quad_block.py:436 ; min over blocks (and ranks) is exact
     ctl->dtmin_bits = DKEY_INF;
+    if (!ctl->allok) ctl->bad = 1;                  // a rank saw an unrealizable state (Euler2D.py:144-152 aborts every rank)
+    ctl->allok = 1ull;
     if (mode == 1) { *out = dt; return; }
     int active = (ctl->t < ctl->t_final) && !ctl->bad;
     ctl->active = active;
@@ -216,7 +218,7 @@ __global__ void k_step_end(Control* ctl) {
 __global__ void __launch_bounds__(256)
 k_geometry(Layout lay, const double* __restrict__ xn, const double* __restrict__ yn,  // (ny+1, nx+1) dense
            double* __restrict__ dxy, double* __restrict__ Lv, double* __restrict__ Lh,
-           double* __restrict__ cdx, double* __restrict__ cdy, int nq, Consts C) {
+           double* __restrict__ cdx, double* __restrict__ cdy, double* __restrict__ pxc, double* __restrict__ pyc, int nq, Consts C) {
     const int nx = lay.nx, ny = lay.ny;
     long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long total = (long long)(ny + 1) * (nx + 1);
@@ -246,6 +248,7 @@ k_geometry(Layout lay, const double* __restrict__ xn, const double* __restrict__
         double yc = 0.25 * (yne + ynw + yse + ysw);
         unsigned o = lay.at(i, j);
         const size_t PL = lay.plane;
+        pxc[o] = xc; pyc[o] = yc;   // QuadMesh.x / .y (quad_mesh.py:172-184), the same doubles the host computes
         // quadrature points (mesh/quadratures.py:56-95): 0.5 * ((p2 - p1) * point + (p2 + p1)), (p1, p2) per side;
         // plane ((q * 4 + f) * 2 + {x, y}) holds the offset of point q of face f from the centroid
         for (int q = 0; q < nq; ++q) {
@@ -292,6 +295,25 @@ k_fill_uniform(Layout lay, double* __restrict__ soa, double u0, double u1, doubl
     unsigned o = lay.at(i, j);
     const size_t PL = lay.plane;
     soa[o] = u0; soa[PL + o] = u1; soa[2 * PL + o] = u2; soa[3 * PL + o] = u3;
+}
+// Two-state initial conditions of the reference's examples (examples/explosion_multi/initial_condition.py:53-59: np.where over
+// the centroid box 3 <= x <= 7 and 3 <= y <= 7; examples/dmr/initial_condition.py:55-58: x <= 0.95): cells whose centroid lies in
+// the closed box [x0, x1] x [y0, y1] get `in`, the others `out` (or stay untouched when has_out == 0).  Comparisons on the
+// same centroid doubles as the host's, so the filled state equals the uploaded one bit for bit.
+__global__ void __launch_bounds__(256)
+k_fill_box(Layout lay, double* __restrict__ soa, const double* __restrict__ xc, const double* __restrict__ yc,
+           double x0, double x1, double y0, double y1, double i0, double i1, double i2, double i3,
+           int has_out, double o0, double o1, double o2, double o3) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = (long long)lay.nx * lay.ny;
+    if (n >= total) return;
+    int i = (int)(n / lay.nx), j = (int)(n - (long long)i * lay.nx);
+    unsigned o = lay.at(i, j);
+    const size_t PL = lay.plane;
+    const double x = xc[o], y = yc[o];
+    const bool inside = (x >= x0) && (x <= x1) && (y >= y0) && (y <= y1);
+    if (inside) { soa[o] = i0; soa[PL + o] = i1; soa[2 * PL + o] = i2; soa[3 * PL + o] = i3; }
+    else if (has_out) { soa[o] = o0; soa[PL + o] = o1; soa[2 * PL + o] = o2; soa[3 * PL + o] = o3; }
 }
 // dense (rows, cols) host-layout array -> plane
 __global__ void __launch_bounds__(256)

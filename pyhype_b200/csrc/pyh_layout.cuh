@@ -34,6 +34,7 @@ struct PlaneOffsets {
     unsigned Lv, cv, sv;           // vertical faces (E/W): length, cos(theta), sin(theta)
     unsigned Lh, ch, sh;           // horizontal faces (N/S)
     unsigned cdx, cdy;             // CFL lengths
+    unsigned xc, yc;               // cell centroids (block.mesh.x / .y): device-side initial conditions (pyh_fill_box)
     unsigned nplanes;
 };
 
@@ -56,6 +57,8 @@ struct Control {
     double t, t_final, dt;
     double coef[PYH_MAX_STAGES * PYH_MAX_STAGES];  // dt * a[s][k]
     unsigned long long dtmin_bits;                 // running min of dx/(|u|+a), dy/(|v|+a) as ordered bits
+    unsigned long long allok;                      // 1 while every state seen is realizable, else 0; directly behind dtmin_bits so
+                                                   // that ONE ncclAllReduce(min, uint64, 2) reduces both across ranks (pyh_comm.cuh)
     long long nsteps;
     int active;      // 1 while t < t_final
     int bad;         // unrealizable state seen

@@ -34,6 +34,7 @@ inline PlaneOffsets plan_offsets(unsigned plane, int S, int nq, const bool need_
     po.Lv = n++ * plane; po.cv = n++ * plane; po.sv = n++ * plane;
     po.Lh = n++ * plane; po.ch = n++ * plane; po.sh = n++ * plane;
     po.cdx = n++ * plane; po.cdy = n++ * plane;
+    po.xc = n++ * plane; po.yc = n++ * plane;
     po.nplanes = n;
     return po;
 }

@@ -83,6 +83,23 @@ static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t str
 }
 #endif
 
+// PYH_LDG (default 0, to be measured): state and geometry loads through ld.global.nc (LDG.E.CONSTANT) instead of the generic
+// LD the compiler emits for pointers fetched from the block table; both planes are read-only for the lifetime of a launch
+#ifndef PYH_LDG
+#define PYH_LDG 0
+#endif
+#if PYH_LDG && !defined(PYH_HOST_TWIN)
+#define PYH_RO(expr) __ldg(&(expr))
+#else
+#define PYH_RO(expr) (expr)
+#endif
+// level 2: the stage's input state as well (NOT with pyh_stage_overlapped: its remote ghost cells land during the launch)
+#if PYH_LDG >= 2 && !defined(PYH_HOST_TWIN)
+#define PYH_ROS(expr) __ldg(&(expr))
+#else
+#define PYH_ROS(expr) (expr)
+#endif
+
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
@@ -160,7 +177,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     auto load_raw = [&](int row, double q[4]) {
         if (exists(row)) {
             unsigned o = (unsigned)((row + 1) * pitch + PADL + jc);
-            q[0] = U[o]; q[1] = U[o + PL]; q[2] = U[o + 2 * PL]; q[3] = U[o + 3 * PL];
+            q[0] = PYH_ROS(U[o]); q[1] = PYH_ROS(U[o + PL]); q[2] = PYH_ROS(U[o + 2 * PL]); q[3] = PYH_ROS(U[o + 3 * PL]);
         } else {
             q[0] = 1.0; q[1] = 0.0; q[2] = 0.0; q[3] = 1.0;
         }
@@ -207,16 +224,16 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         double gdx[NQ][4], gdy[NQ][4];
         if (doB && (r < ny)) {
             const unsigned oE = o + 1, oN = o + pitch;
-            gLE = G[po.Lv + oE]; gLW = G[po.Lv + o]; gLN = G[po.Lh + oN]; gLS = G[po.Lh + o];
-            gcE = G[po.cv + oE]; gcW = G[po.cv + o]; gcN = G[po.ch + oN]; gcS = G[po.ch + o];
-            gsE = G[po.sv + oE]; gsW = G[po.sv + o]; gsN = G[po.sh + oN]; gsS = G[po.sh + o];
-            gA = G[po.A + o];
+            gLE = PYH_RO(G[po.Lv + oE]); gLW = PYH_RO(G[po.Lv + o]); gLN = PYH_RO(G[po.Lh + oN]); gLS = PYH_RO(G[po.Lh + o]);
+            gcE = PYH_RO(G[po.cv + oE]); gcW = PYH_RO(G[po.cv + o]); gcN = PYH_RO(G[po.ch + oN]); gcS = PYH_RO(G[po.ch + o]);
+            gsE = PYH_RO(G[po.sv + oE]); gsW = PYH_RO(G[po.sv + o]); gsN = PYH_RO(G[po.sh + oN]); gsS = PYH_RO(G[po.sh + o]);
+            gA = PYH_RO(G[po.A + o]);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    gdx[q][f] = G[po.dxy + ((q * 4 + f) * 2) * PL + o];
-                    gdy[q][f] = G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o];
+                    gdx[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2) * PL + o]);
+                    gdy[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o]);
                 }
             }
         }
@@ -249,23 +266,23 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 double (&dx)[NQ][4] = gdx;
                 double (&dy)[NQ][4] = gdy;
 #else
-                double LE = G[po.Lv + oE], LW = G[po.Lv + o], LN = G[po.Lh + oN], LS = G[po.Lh + o];
+                double LE = PYH_RO(G[po.Lv + oE]), LW = PYH_RO(G[po.Lv + o]), LN = PYH_RO(G[po.Lh + oN]), LS = PYH_RO(G[po.Lh + o]);
 #if PYH_FOLD_POW2
                 // half face weights: (0.5 (q + qE)) * xlE == (q + qE) * (0.5 xlE), both scalings exact (pyh_math.cuh)
                 LE = 0.5 * LE; LW = 0.5 * LW; LN = 0.5 * LN; LS = 0.5 * LS;
 #endif
-                double xlE = LE * G[po.cv + oE], xlW = LW * (-G[po.cv + o]);
-                double xlN = LN * G[po.ch + oN], xlS = LS * (-G[po.ch + o]);
-                double ylE = LE * G[po.sv + oE], ylW = LW * (-G[po.sv + o]);
-                double ylN = LN * G[po.sh + oN], ylS = LS * (-G[po.sh + o]);
-                double Acell = G[po.A + o];
+                double xlE = LE * PYH_RO(G[po.cv + oE]), xlW = LW * (-PYH_RO(G[po.cv + o]));
+                double xlN = LN * PYH_RO(G[po.ch + oN]), xlS = LS * (-PYH_RO(G[po.ch + o]));
+                double ylE = LE * PYH_RO(G[po.sv + oE]), ylW = LW * (-PYH_RO(G[po.sv + o]));
+                double ylN = LN * PYH_RO(G[po.sh + oN]), ylS = LS * (-PYH_RO(G[po.sh + o]));
+                double Acell = PYH_RO(G[po.A + o]);
                 double dx[NQ][4], dy[NQ][4];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
 #pragma unroll
                     for (int f = 0; f < 4; ++f) {
-                        dx[q][f] = G[po.dxy + ((q * 4 + f) * 2) * PL + o];
-                        dy[q][f] = G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o];
+                        dx[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2) * PL + o]);
+                        dy[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o]);
                     }
                 }
 #endif
@@ -383,7 +400,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         // ---- C(r): west face J = j of row r ----------------------------------------------------------
         double IW[4] = {0.0, 0.0, 0.0, 0.0};
         if (full && doV) {
-            const double cf = G[po.cv + o], sf = G[po.sv + o], Lf = G[po.Lv + o];
+            const double cf = PYH_RO(G[po.cv + o]), sf = PYH_RO(G[po.sv + o]), Lf = PYH_RO(G[po.Lv + o]);
             // riemann_flux returns flux_scale(FLUX) * F (pyh_math.cuh); the face length absorbs the factor, exactly
             const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;     // one point:  L * (0 + 2 F)
             const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;     // 2, 3 points: L * sum_p w_p F_p
@@ -453,7 +470,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             double dA = 1.0, dS0[4] = {0.0, 0.0, 0.0, 0.0}, dS1[4] = {0.0, 0.0, 0.0, 0.0};
             auto load_d = [&]() {
                 const unsigned om_ = o - pitch;
-                dA = G[po.A + om_];
+                dA = PYH_RO(G[po.A + om_]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     dS0[k] = (plan.ntargets > 0) ? base[plan.t[0].src + k * PL + om_] : 0.0;
@@ -464,7 +481,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 #if PYH_D_EARLY == 2
             if (r - 1 >= i0) load_d();
 #endif
-            const double cf = G[po.ch + o], sf = G[po.sh + o], Lf = G[po.Lh + o];
+            const double cf = PYH_RO(G[po.ch + o]), sf = PYH_RO(G[po.sh + o]), Lf = PYH_RO(G[po.Lh + o]);
             const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;
             const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;
             double IS[4];
@@ -534,7 +551,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 #if PYH_D_EARLY
                 const double a = dA;
 #else
-                const double a = G[po.A + om];
+                const double a = PYH_RO(G[po.A + om]);
 #endif
                 double Rk[4];
                 auto resid = [&](auto tag) -> bool {

@@ -1,4 +1,10 @@
-"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink) as transport.
+"""Multi-GPU plumbing: one process per GPU.
+
+The shipped transport lives in the C layer (``pyh_comm_init``, pyhype_b200/csrc/pyh_comm.cuh: NCCL over NVLink bound
+with dlopen; the strip exchange and the dt all-reduce are part of the CUDA graph of one time step).  This module holds
+the block -> rank rule, the helper that distributes the NCCL id, and a HOST-DRIVEN transport over ``torch.distributed``
+(``HaloExchanger`` / ``advance``) that drives any engine with the C ABI's pack / unpack contract -- it is what the CPU
+arm of bench.py and the gloo tests use with the oracle-backed stand-in engine.
 
 Replaces the reference's mpi4py layer (pyhype/blocks/ghost.py:169-241 Isend/Irecv per ghost
 strip, pyhype/blocks/base.py:454-465 Waitall, pyhype/solvers/base.py:128-131 gather+bcast of dt):
@@ -61,6 +67,19 @@ def init_nccl(device_index):
     if opts is not None:
         kw["pg_options"] = opts
     dist.init_process_group("nccl", **kw)
+
+
+def share_unique_id(make_id, rank, world):
+    """Hand rank 0's 128-byte NCCL id to every rank.  The side channel is ``torch.distributed`` (already initialised by the
+    caller, or a CPU-only gloo group created here from the torchrun environment) -- control plane only: the strips and the
+    dt reduction travel through the NCCL communicator the C layer owns (``pyh_comm_init``)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
 
 
 def exchange_plan(slots, owner, rank):

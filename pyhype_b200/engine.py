@@ -123,6 +123,14 @@ class Engine:
         v = _c(np.asarray(state, dtype=np.float64).reshape(4))
         check(self.lib.pyh_fill_uniform(self._ctx, int(gid), _dp(v)))
 
+    def fill_box(self, gid, x0, x1, y0, y1, inside, outside=None):
+        """Cells of block ``gid`` whose centroid lies in the closed box [x0, x1] x [y0, y1] become the conservative 4-vector
+        ``inside``, the others ``outside`` (None: left as they are).  No upload: evaluated on the device's centroids."""
+        vi = _c(np.asarray(inside, dtype=np.float64).reshape(4))
+        vo = None if outside is None else _c(np.asarray(outside, dtype=np.float64).reshape(4))
+        check(self.lib.pyh_fill_box(self._ctx, int(gid), float(x0), float(x1), float(y0), float(y1), _dp(vi),
+                                    None if vo is None else _dp(vo)))
+
     def download(self, gid, out=None):
         """Conservative state of block ``gid`` as (ny, nx, 4); ``out`` may be a caller-owned
         (e.g. pinned) C-contiguous float64 array to receive it without an extra copy."""
@@ -230,7 +238,30 @@ class Engine:
         check(self.lib.pyh_realizable(self._ctx, C.byref(ok)))
         return bool(ok.value)
 
-    # -- remote halo ------------------------------------------------------------------------------------
+    # -- multi-rank transport owned by the library (NCCL bound inside the C layer) ------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id (rank 0 creates it; the host hands it to every rank through any side channel)."""
+        buf = C.create_string_buffer(128)
+        check(_lib.load().pyh_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id: bytes, owner):
+        """Collective.  ``owner``: {global block id: rank} or a sequence indexed by block id.  Afterwards apply_bc /
+        step / run / get_dt / realizable are collective calls and exchange the remote ghost strips themselves."""
+        n = len(owner)
+        table = (C.c_int32 * n)(*[int(owner[g]) for g in range(n)])
+        idbuf = C.create_string_buffer(bytes(unique_id), 128)
+        check(self.lib.pyh_comm_init(self._ctx, int(rank), int(world), idbuf, table, n))
+        self.comm_world = int(world)
+
+    def comm_info(self):
+        r, w, n = C.c_int32(), C.c_int32(), C.c_int32()
+        d = C.c_int64()
+        check(self.lib.pyh_comm_info(self._ctx, C.byref(r), C.byref(w), C.byref(n), C.byref(d)))
+        return dict(rank=r.value, world=w.value, messages=n.value, doubles_per_exchange=d.value)
+
+    # -- remote halo (host-driven transport: the pack / unpack halves of the exchange) ----------------------------
     def halo_slots(self):
         n = C.c_int64()
         nd = C.c_int64()

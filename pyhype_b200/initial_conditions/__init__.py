@@ -1,4 +1,5 @@
 from .base import InitialCondition
+from .box import BoxInitialCondition
 from .supersonic_flood import SupersonicFloodInitialCondition
 
-__all__ = ["InitialCondition", "SupersonicFloodInitialCondition"]
+__all__ = ["InitialCondition", "BoxInitialCondition", "SupersonicFloodInitialCondition"]

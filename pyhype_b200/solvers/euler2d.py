@@ -12,7 +12,7 @@ import numpy as np
 
 from ..blocks import SIDES, QuadBlock
 from ..boundary_conditions.base import BoundaryCondition, PrimitiveDirichletBC
-from ..distributed import advance, distribute_blocks, world
+from ..distributed import distribute_blocks, share_unique_id, world
 from ..engine import FLUX_IDS, LIMITER_IDS, Engine
 from ..mesh.base import MeshGenerator
 from ..states import ConservativeState, PrimitiveState, RealizabilityException
@@ -182,23 +182,13 @@ class Euler2D:
             self._engine.add_block(g, blk.mesh, blk.info.neighbors, bcs, local_gids=local)
             blk._attach(self._engine)
         self._engine.finalize()
-        self._halo = None
         self._writer = None
         self._in_solve = False
         if self._world > 1:
-            import torch
-            import torch.distributed as dist
-
-            from ..distributed import HaloExchanger
-
-            if not dist.is_initialized():
-                from ..distributed import init_nccl
-
-                init_nccl(self._device)
-            self._torch = torch
-            self._stream = torch.cuda.ExternalStream(self._engine.stream(), device=torch.device("cuda", self._device))
-            with torch.cuda.stream(self._stream):
-                self._halo = HaloExchanger(self._engine, owner, self.cpu)
+            # the transport (NCCL strip exchange + dt all-reduce) lives in the C layer; torch.distributed only carries the
+            # 128-byte communicator id (mpi4py's role in the reference: blocks/ghost.py:169-241, solvers/base.py:128-131)
+            uid = share_unique_id(Engine.comm_unique_id, self.cpu, self._world)
+            self._engine.comm_init(self.cpu, self._world, uid, owner)
         self._logger.info("\n\tFinished setting up solver")
 
     def __str__(self):
@@ -226,11 +216,7 @@ class Euler2D:
     def get_dt(self) -> float:
         """solvers/base.py:114-136"""
         self._flush_host_states()
-        if self._halo is None:
-            return self._engine.get_dt(self.t, self.t_final)
-        with self._torch.cuda.stream(self._stream):
-            dt = float(self._halo.global_dt().item())
-        return self.t_final - self.t if self.t_final - self.t < dt else dt
+        return self._engine.get_dt(self.t, self.t_final)   # collective on >1 rank: global minimum
 
     def solve(self):
         self._pre_process_solve()
@@ -249,22 +235,12 @@ class Euler2D:
         for block in self.blocks:
             block.state.push_if_touched()
 
-    def _wait_halo(self):
-        if self._halo is not None:
-            with self._torch.cuda.stream(self._stream):
-                self._halo.wait()
-
     def _mark_device_newer(self):
         for block in self.blocks:
             block.state.mark_device_newer()
 
     def _refresh_ghosts(self):
-        if self._halo is not None:
-            with self._torch.cuda.stream(self._stream):
-                self._halo.exchange()
-                self._engine.apply_bc()
-        else:
-            self._engine.apply_bc()
+        self._engine.apply_bc()   # remote strips (if any) are exchanged inside
 
     def _pre_process_solve(self):
         self._logger.info("\t>>> Setting Initial Conditions")
@@ -286,19 +262,11 @@ class Euler2D:
     def _update_solution_blocks(self, dt: float) -> None:
         """ExplicitRungeKutta.integrate (time_marching/explicit_runge_kutta.py:47-80)"""
         self._flush_host_states()
-        if self._halo is None:
-            self._engine.step(dt)
-        else:
-            with self._torch.cuda.stream(self._stream):
-                advance(self._engine, self._halo, self._engine.num_stages, dt=dt)
+        self._engine.step(dt)
         self._mark_device_newer()
 
     def _realizability_check(self):
-        ok = self._engine.realizable()
-        if self._halo is not None:
-            flag = self._torch.tensor([0 if ok else 1], device=f"cuda:{self._device}")
-            self._torch.distributed.all_reduce(flag)
-            ok = int(flag.item()) == 0
+        ok = self._engine.realizable()   # reduced over all ranks by the library
         if not ok:
             msg = "ConservativeState has unrealizable values (rho <= 0 or e <= 0)"
             self._logger.error(msg)
@@ -323,36 +291,31 @@ class Euler2D:
             profiler = cProfile.Profile()
             profiler.enable()
         writes = self.config.write_solution and self.config.write_solution_mode == "every_n_timesteps"
-        if self._halo is not None:
-            while self.t < self.t_final:
-                if self.num_time_step % 50 == 0:
-                    self._log_progress()
-                self.step()
-        else:
-            # device-resident loop between output points: dt, t and the step counter stay on the GPU
-            self._flush_host_states()
-            while self.t < self.t_final:
-                self._log_progress()
-                if writes:
-                    every = self.config.write_every_n_timesteps
-                    nxt = (every - self.num_time_step % every) + 1 if self.num_time_step % every else 1
-                else:
-                    nxt = -1
-                # the reference writes *after* the update of a step whose counter is a multiple of
-                # `every`, before the counter is incremented (Euler2D.py:206-210)
-                t, n, bad, _ = self._engine.run(self.t, self.t_final, max_steps=nxt, poll_every=50)
-                self._mark_device_newer()
-                if bad:
-                    msg = "ConservativeState has unrealizable values (rho <= 0 or e <= 0)"
-                    self._logger.error(msg)
-                    raise RealizabilityException(msg)
-                if n == 0:
-                    break
-                self.num_time_step += n - 1
-                if writes:
-                    self.write_solution()
-                self.num_time_step += 1
-                self.t = t
+        # device-resident loop between output points: dt, t and the step counter stay on the GPU; on >1 rank the strip
+        # exchange and the dt all-reduce are part of the same CUDA graph and every rank sees the same t / step count
+        self._flush_host_states()
+        while self.t < self.t_final:
+            self._log_progress()
+            if writes:
+                every = self.config.write_every_n_timesteps
+                nxt = (every - self.num_time_step % every) + 1 if self.num_time_step % every else 1
+            else:
+                nxt = -1
+            # the reference writes *after* the update of a step whose counter is a multiple of
+            # `every`, before the counter is incremented (Euler2D.py:206-210)
+            t, n, bad, _ = self._engine.run(self.t, self.t_final, max_steps=nxt, poll_every=50)
+            self._mark_device_newer()
+            if bad:
+                msg = "ConservativeState has unrealizable values (rho <= 0 or e <= 0)"
+                self._logger.error(msg)
+                raise RealizabilityException(msg)
+            if n == 0:
+                break
+            self.num_time_step += n - 1
+            if writes:
+                self.write_solution()
+            self.num_time_step += 1
+            self.t = t
         if profiler is not None:
             import pstats
 

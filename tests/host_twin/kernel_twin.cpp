@@ -110,7 +110,7 @@ struct Twin {
             put(cos_h + b * nh, slab + po.ch, ny + 1, nx);
             put(sin_h + b * nh, slab + po.sh, ny + 1, nx);
             launch(dim3(cdivu((long long)nn, 256)), 256, false, [&] {
-                k_geometry(lay, nodes_x + b * nn, nodes_y + b * nn, slab + po.dxy, slab + po.Lv, slab + po.Lh, slab + po.cdx, slab + po.cdy, nq, C);
+                k_geometry(lay, nodes_x + b * nn, nodes_y + b * nn, slab + po.dxy, slab + po.Lv, slab + po.Lh, slab + po.cdx, slab + po.cdy, slab + po.xc, slab + po.yc, nq, C);
             });
             BlkDev& D = blks[b];
             std::memset(&D, 0, sizeof(D));
@@ -251,7 +251,7 @@ int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int 
     tb.nstages = S;
     for (int i = 0; i < PYH_MAX_STAGES * PYH_MAX_STAGES; ++i) tb.a[i] = tab[i];
     Control& ctl = T.ctl;
-    ctl.t = t0; ctl.t_final = t_final; ctl.dtmin_bits = DKEY_INF; ctl.active = 1; ctl.nsteps = 0; ctl.bad = 0;
+    ctl.t = t0; ctl.t_final = t_final; ctl.dtmin_bits = DKEY_INF; ctl.allok = 1ull; ctl.active = 1; ctl.nsteps = 0; ctl.bad = 0;
     ctl.dts = dts_out; ctl.dts_cap = max_steps;
     int i0 = 0, i1 = 1, i2 = 2, cur = 0;
     T.ghost(i0);

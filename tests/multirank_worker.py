@@ -22,18 +22,22 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     nx, ny = 26, 22
-    config = em_config(nx=nx, ny=ny, t_final=0.004, initial_condition=ExplosionInitialCondition())
+    integ = os.environ.get("PYH_TEST_INTEGRATOR", "RK4")
+    cfl = 0.3 if integ == "ExplicitEuler1" else 0.7
+    config = em_config(nx=nx, ny=ny, t_final=0.004, initial_condition=ExplosionInitialCondition(), time_integrator=integ, CFL=cfl)
     # PYH_TEST_LAYOUT = "NBXxNBY": default 2x4 (rank boundaries between block rows); "2x1" with 2 ranks puts the rank
     # boundary on an east / west edge
     nbx, nby = (int(v) for v in os.environ.get("PYH_TEST_LAYOUT", "2x4").split("x"))
     mesh = em_mesh() if (nbx, nby) == (2, 4) else cases.em_mesh(nbx=nbx, nby=nby)
     sim = Euler2D(config=config, mesh_config=mesh)
     sim.solve()
-    prob = cases.build_oracle(mesh.dict if hasattr(mesh, "dict") else mesh, nx, ny, cases.explosion_ic)
+    prob = cases.build_oracle(mesh.dict if hasattr(mesh, "dict") else mesh, nx, ny, cases.explosion_ic, integrator=integ, CFL=cfl)
     t, dts = prob.run(0.0, 0.004 * 343.0)
     assert sim.num_time_step == len(dts) and sim.t == t, (sim.num_time_step, len(dts))
     mine = [b.global_block_num for b in sim.blocks]
     assert len(mine) == (nbx * nby) // world or world > nbx * nby
+    if world > nbx * nby:
+        assert len(mine) == (1 if rank < nbx * nby else 0)
     for block in sim.blocks:
         ref = prob.blocks[block.global_block_num]
         assert np.array_equal(block.state.data, ref.U), f"rank {rank} block {block.global_block_num}"

@@ -1,6 +1,12 @@
 """BASELINE.json's named configurations at their NAMED sizes against fingerprints of the unmodified reference
 (tests/golden/named/*.npz, written by oracle/make_named_fingerprints.py in the build container):
 
+* examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall, 15 degree ramp), with
+  the shipped HLLL flux and with the Roe flux BASELINE.json names, first 50 steps;
+* examples/jet at its shipped size (9 stacked blocks of 1080 x 60, slip walls + Dirichlet inlet), shipped HLLL flux, first 50
+  steps -- and with the HLLE flux BASELINE.json names (two-edit patched reference), whose run the reference itself aborts
+  in step 17 with an unrealizable state: the engine must reproduce steps 5, 10, 16 AND report the abort in step 17;
+
 * explosion_multi exactly as shipped -- 2 x 4 blocks of 150 x 150, Roe + Venkatakrishnan + Green-Gauss, RK4, CFL 0.7,
   reflection walls -- from the initial condition to t_final = 0.07 (1604 steps);
 * the DMR scheme -- HLLL + Venkatakrishnan, primitive reconstruction, RK2, CFL 0.4 -- on 4 blocks of 500 x 500, the
@@ -40,7 +46,7 @@ class Named:
         self.name = name
         self.gids = self.meta["gids"]
         self.nx, self.ny, self.stride = self.meta["nx"], self.meta["ny"], self.meta["stride"]
-        self.blocks = getattr(cases, self.meta["mesh"])()
+        self.blocks = getattr(cases, self.meta["mesh"])(*self.meta.get("mesh_args", []))
         self.ic = getattr(cases, self.meta["ic"])
         self.dts = self.z["dts"]
         self._u0 = None
@@ -69,8 +75,11 @@ class Named:
             assert value_digest(U) == self.meta["digests"][f"{n}_{g}"], (self.name, n, g, np.abs(sub - ref).max())
 
 
+ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle"]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["em", "dmr"])
+@pytest.mark.parametrize("name", ALL_NAMED)
 def test_named_config_at_named_size_reproduces_the_reference(name):
     fp = Named(name)
     eng = cases.build_engine(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
@@ -87,14 +96,22 @@ def test_named_config_at_named_size_reproduces_the_reference(name):
         if fp.meta["reached_t_final"]:
             assert not (t < fp.meta["t_final_nd"])
             assert eng.run(t, fp.meta["t_final_nd"], max_steps=4, poll_every=1)[1] == 0      # the run is over: no further step
+        if "aborts_in_step" in fp.meta:
+            # the reference's realizability check stops the run in the next step (Euler2D.py:144-152); the device loop takes
+            # that step, flags the state and stops (it reports up to `poll_every` steps late, never silently)
+            t2, done, bad, _ = eng.run(t, fp.meta["t_final_nd"], max_steps=3, poll_every=1)
+            assert bad and done >= 1, (name, done, bad)
+            assert not eng.realizable()
     finally:
         eng.close()
 
 
-@pytest.mark.parametrize("name", ["em", "dmr"])
+@pytest.mark.parametrize("name", ALL_NAMED)
 def test_oracle_restatement_at_named_size_first_checkpoint(name):
     fp = Named(name)
     n = fp.meta["checkpoints"][0]
+    if name.startswith("wedge"):
+        n = fp.meta["checkpoints"][-1]          # 2 x 60^2: all 50 steps cost a second
     prob = cases.build_oracle(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
     t, dts = prob.run(0.0, fp.meta["t_final_nd"], max_steps=n)
     assert np.array_equal(np.asarray(dts), fp.dts[:n])

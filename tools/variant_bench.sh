@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 for spec in "$@"; do
   set -- $spec
   name=$1; shift
-  out=$(env "$@" PYH_LIB_PATH=gpurun_variants/libpyh_${name}.so python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>&1 | tail -1)
+  out=$(env "$@" PYH_LIB_PATH=gpurun_variants/libpyh_${name}.so python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-named --sustain-steps 0 2>&1 | tail -1)
   echo "$spec :: $(echo "$out" | python -c 'import json,sys
 try:
     d=json.loads(sys.stdin.read()); print("value %.4g ms/step %.3f stage_ms %.4f" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_avg"]))

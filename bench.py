@@ -29,45 +29,12 @@ import numpy as np  # noqa: E402
 
 GAMMA = 1.4
 A_INF = 343.0
-BLOCK_LEN = 1.25  # length units per block side
 
 
 # ---------------------------------------------------------------------------------------------
 # workload definition (shared by both arms)
 # ---------------------------------------------------------------------------------------------
-def ws_mesh(n_gpus, blocks_per_gpu):
-    from pyhype_b200.mesh.rectangular import RectagularMeshGenerator
-
-    return RectagularMeshGenerator.generate(
-        BCE=["Reflection"], BCW=["Reflection"], BCN=["Reflection"], BCS=["Reflection"],
-        east=BLOCK_LEN * blocks_per_gpu, west=0.0, north=BLOCK_LEN * n_gpus, south=0.0,
-        n_blocks_horizontal=blocks_per_gpu, n_blocks_vertical=n_gpus,
-    ).dict
-
-
-def ws_ic(x, y, width, height):
-    """Explosion box over the central 40 % of the domain (explosion_multi states), conservative,
-    non-dimensional (examples/explosion/initial_condition.py:35-60)."""
-    inside = (x >= 0.3 * width) & (x <= 0.7 * width) & (y >= 0.3 * height) & (y <= 0.7 * height)
-
-    def cons(rho, p):
-        e = p / (GAMMA - 1) + 0.0
-        return np.array([rho / 1.0, 0.0, 0.0, e / (1.0 * A_INF**2)])
-
-    hi, lo = cons(4.6968, 404400.0), cons(1.1742, 101100.0)
-    return np.where(inside[..., None], hi, lo)
-
-
-def ws_ic_smooth(x, y, width, height):
-    """Rounding-robust smooth field (IC-B): every face carries a genuine Riemann problem
-    (diagnostic runs with --ic smooth; the headline workload is the explosion box)."""
-    rho = 1.2 + 0.3 * np.sin(0.7 * x + 0.3) * np.cos(0.45 * y + 0.1)
-    u = 30 * np.cos(0.5 * x) * np.sin(0.35 * y + 0.2)
-    v = -25 * np.sin(0.4 * x + 0.5) * np.cos(0.3 * y)
-    p = 101325 * (1 + 0.2 * np.cos(0.6 * x - 0.2) * np.sin(0.5 * y + 0.4))
-    ek = 0.5 * rho * (u * u + v * v)
-    U = np.stack((rho, rho * u, rho * v, p / (GAMMA - 1) + ek), axis=-1)
-    return U / np.array([1.0, A_INF, A_INF, A_INF**2])
+from pyhype_b200.examples import WS_BLOCK_LEN as BLOCK_LEN, ws_ic, ws_ic_smooth, ws_mesh  # noqa: E402  (the inputs tests/ pins to the reference)
 
 
 BYTES_PER_CELL_STEP = {"RK4": 512.0, "RK2": 160.0, "ExplicitEuler1": 64.0}  # SURVEY.md section 8d
@@ -283,6 +250,7 @@ def run_named(torch, name, device, steps, peak):
     gids = sorted(blocks)
     eng, states, nstages = build_engine(blocks, gids, nx, ny, scheme, device, ic=ic, pin=True)
     cells = len(gids) * nx * ny
+    shape = eng.march_shape()
     timer = StreamTimer(torch, eng, device)
 
     def load_ic():
@@ -328,6 +296,7 @@ def run_named(torch, name, device, steps, peak):
     return {
         "workload": NAMED[name]["title"], "cells_total": cells, "stages_per_step": nstages, "steps": int(k),
         "value": value, "unit": "cell-stage updates/s", "ms_per_step": ms / max(k, 1), "gpu_launches": int(launches),
+        "stage_kernel_shape": {"lanes": shape[0], "rows_per_strip": shape[1]},
         "parity": {"bit_identical_to_reference": bool(parity_ok), "checkpoints": meta["checkpoints"],
                    "what": "every dt and the sha256-by-value of every block state at each checkpoint vs the unmodified reference's fingerprint (" + meta["generator"] + ")"},
         "e2e": {"value": cells * nstages * k / e2e_s, "unit": "cell-stage updates/s", "h2d_bytes_per_step": cells * 32 / max(k, 1),

@@ -14,8 +14,8 @@
  *     "aos" state arrays are (ny, nx, 4) with the last axis [rho, rho*u, rho*v, e], exactly the
  *     reference's block.state.data layout (pyhype/fvm/base.py:210-212);
  *   - side order is always E, W, N, S (pyhype/utils/utils.py:229-237);
- *   - one context drives one GPU (one process per GPU; ranks exchange ghost strips through the
- *     pack/unpack entry points, the transport itself is NCCL in the host layer);
+ *   - one context drives one GPU (one process per GPU); ranks exchange ghost strips and reduce the time step through
+ *     the library's own NCCL communicator (pyh_comm_init) -- or, host-driven, through the pack / unpack entry points;
  *   - a context is not thread-safe; the caller owns host buffers, which are only touched during
  *     the call; device pointers handed in must belong to the context's device.
  */
@@ -168,22 +168,6 @@ int pyh_step_begin(void* ctx, double dt);
 int pyh_step_begin_dev(void* ctx, const double* dev_dt);
 int pyh_stage(void* ctx, int stage);
 int pyh_step(void* ctx, double dt);
-/* Overlap of the remote exchange with the stage kernel (the reference posts Isend/Irecv and only then
- * applies local BCs, blocks/base.py:454-465; here the overlap partner is the residual itself):
- *   pyh_unpack_halo_on(recv, stream): pyh_unpack_halo on a caller-owned stream (a cudaStream_t value, e.g.
- *     the one the NCCL receives complete on), followed by an epoch stamp in the device control block.
- *   pyh_stage_overlapped(s): ONE launch of the stage kernel whose row strips are the slowest dispatch
- *     dimension with the strips on a block's south / north edge dispatched last; thread blocks that read
- *     remotely owned ghost cells wait (normally zero time) for the stamp of the latest pyh_unpack_halo_on,
- *     all others never wait.  The caller must have enqueued that unpack (on any stream) before calling,
- *     and must not touch the ghost frames from the compute stream meanwhile.
- *   pyh_overlap_info: whether the context has remote edges, and how many thread blocks
- *     per launch read remote ghost cells (the host falls back to the blocking order when they could fill
- *     the device on their own). */
-int pyh_stage_overlapped(void* ctx, int stage);
-int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream);
-int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas);
-
 /* Multi-rank transport owned by the library: NCCL over NVLink, one context (= one GPU) per rank.  Replaces the
  * mpi4py calls of the reference: Isend / Irecv per ghost strip (pyhype/blocks/ghost.py:169-241), the Waitall of
  * Blocks.apply_boundary_condition (pyhype/blocks/base.py:454-465) and the gather + bcast of the time step
@@ -193,8 +177,13 @@ int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas);
  *                        (Blocks.distribute_blocks_to_processes, pyhype/blocks/base.py:473-513).
  * Once initialised, pyh_apply_bc, pyh_step, pyh_run, pyh_local_dt, pyh_get_dt and pyh_realizable are COLLECTIVE:
  * every rank must call them in the same order.  Each ghost refresh packs the edge strips remote neighbours need,
- * exchanges them in ONE grouped ncclSend / ncclRecv batch and unpacks them, on the context's stream; the CFL minimum
- * and the realizability flag are reduced by one 16-byte ncclAllReduce(min).  A rank may own no blocks. */
+ * exchanges them in ONE grouped ncclSend / ncclRecv batch and unpacks them; the CFL minimum and the realizability flag
+ * are reduced by one 16-byte ncclAllReduce(min).  Inside pyh_step / pyh_run the exchange is OVERLAPPED with the residual
+ * (the reference posts Isend / Irecv and only then applies the local BCs, blocks/base.py:454-465; here the overlap partner is
+ * the stage kernel itself): every stage is launched as thin edge strips -- the first / last rows and column strips of each
+ * block, whose results the neighbour ranks need -- on a high-priority side stream, followed there by pack -> NCCL -> unpack,
+ * while the interior launch runs on the compute stream; both join before the local ghost copies (PYH_NO_HALO_OVERLAP=1
+ * selects the blocking order for diagnostics).  A rank may own no blocks. */
 #define PYH_COMM_ID_BYTES 128
 int pyh_comm_unique_id(void* id_out);
 int pyh_comm_init(void* ctx, int32_t rank, int32_t world, const void* id, const int32_t* owner, int32_t nblocks_total);
@@ -217,6 +206,8 @@ int pyh_residual(void* ctx, int gid, double* aos_out);
 typedef enum { PYH_DBG_GRAD_X = 0, PYH_DBG_GRAD_Y = 1, PYH_DBG_PHI = 2 } pyh_debug_what;
 int pyh_debug_fetch(void* ctx, int gid, int what, double* aos_out);
 
+/* Strip shape the stage kernel runs with: lanes per thread block (lanes - 4 output columns) x rows per strip. */
+int pyh_march_shape(void* ctx, int32_t* lanes, int32_t* rows);
 /* Counters for bench.py: kernels launched by this context since creation. */
 int pyh_launch_count(void* ctx, int64_t* n);
 /* The CUDA stream all of the context's kernels are launched on (as a cudaStream_t value). */

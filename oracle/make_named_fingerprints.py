@@ -42,6 +42,18 @@ CASES = {
                 cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.4, reconstruction_type="primitive",
                          t_final=0.25),
                 what="examples/dmr scheme at BASELINE.json's 500x500 blocks (shipped: 50x50), first 40 steps"),
+    # BASELINE.json configs[4] towards the HEADLINE BLOCK SIZE: one block of the weak-scaling mesh (bench.py's workload is 8 blocks
+    # of 2048 x 2048 per GPU; the reference's object model is killed by the container's memory limit at 2048 x 2048, so the
+    # reference pins 1024 x 1024 and oracle/make_ws2048_fingerprint.py pins 2048 x 2048 with the numpy restatement), explosion box
+    # inside, Roe + Venkatakrishnan, RK4, CFL 0.7; the first 2 steps
+    "ws1024": dict(mesh="ws_mesh", mesh_args=(1, 1), ic="ws_ic_1x1", nx=1024, ny=1024, stride=32, checkpoints=[1, 2],
+                   cfg=dict(t_final=0.07),
+                   what="synthetic weak-scaling explosion, one block of 1024 x 1024 (the largest the unmodified reference fits in this container), first 2 RK4 steps"),
+    # the headline block size itself, pinned by the NUMPY RESTATEMENT (oracle/muscl_oracle.py, which the cases above and the 28
+    # fixtures pin to the reference): the reference's object model does not fit 2048 x 2048 in this container
+    "ws2048": dict(mesh="ws_mesh", mesh_args=(1, 1), ic="ws_ic_1x1", nx=2048, ny=2048, stride=64, checkpoints=[1], by_oracle=True,
+                   cfg=dict(t_final=0.07),
+                   what="synthetic weak-scaling explosion at the headline block size: one block of 2048 x 2048, first RK4 step, by the numpy oracle"),
     # BASELINE.json configs[2]: examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall,
     # 15 degree ramp), with the shipped flux (HLLL) and with the one BASELINE.json names (Roe); first 50 steps
     "wedge": dict(mesh="wedge_mesh", mesh_args=(60,), ic="wedge_ic", nx=60, ny=60, stride=6, checkpoints=[10, 50],
@@ -66,6 +78,40 @@ def value_digest(U):
     return hashlib.sha256((np.ascontiguousarray(U) + 0.0).tobytes()).hexdigest()
 
 
+class OracleRun:
+    """RefRun's interface (oracle/refharness.py) on top of the numpy restatement, for sizes the reference cannot hold."""
+
+    class _Blk:
+        def __init__(self, g, b):
+            self.global_block_num, self._b = g, b
+
+        @property
+        def state(self):
+            return type("S", (), {"data": self._b.U})()
+
+    class _Solver:
+        pass
+
+    def __init__(self, cases, blocks, c, ic, config):
+        recon = c["cfg"].get("reconstruction_type", "conservative")
+        self.prob = cases.build_oracle(blocks, c["nx"], c["ny"], ic, flux=config.fvm_flux_function_type, limiter=config.fvm_slope_limiter_type,
+                                       recon=recon, integrator=config.time_integrator, CFL=config.CFL)
+        self.solver = self._Solver()
+        self.solver.t = 0.0
+        self.solver.t_final = config.t_final * 343.0
+        self.dts = []
+
+    @property
+    def blocks(self):
+        return [self._Blk(g, b) for g, b in sorted(self.prob.blocks.items())]
+
+    def step(self, n=1):
+        t, dts = self.prob.run(self.solver.t, self.solver.t_final, max_steps=n)
+        self.solver.t = t
+        self.dts += dts
+        return self
+
+
 def main(name):
     import cases
     from make_golden import ref_blocks
@@ -82,13 +128,17 @@ def main(name):
             block.state.data = np.ascontiguousarray(ic(block.mesh.x[:, :, 0], block.mesh.y[:, :, 0]))
 
     config = rh.make_config(nx=c["nx"], ny=c["ny"], initial_condition=IC(), **c["cfg"])
-    run = rh.RefRun(config, ref_blocks(blocks))
+    if c.get("by_oracle"):
+        run = OracleRun(cases, blocks, c, ic, config)
+    else:
+        run = rh.RefRun(config, ref_blocks(blocks))
     t_final = float(run.solver.t_final)
     out, meta = {}, dict(name=name, what=c["what"], nx=c["nx"], ny=c["ny"], stride=c["stride"], mesh=c["mesh"], mesh_args=list(c.get("mesh_args", ())), ic=c["ic"],
                          flux=config.fvm_flux_function_type, limiter=config.fvm_slope_limiter_type,
                          recon=c["cfg"].get("reconstruction_type", "conservative"), integrator=config.time_integrator,
                          CFL=config.CFL, t_final_nd=t_final, gids=sorted(blocks), checkpoints=[], digests={}, raw_sha16={},
-                         generator="oracle/make_named_fingerprints.py on the unmodified reference" + (" + HLLE 2-edit patch" if c.get("patch_hlle") else ""))
+                         generator=("oracle/make_named_fingerprints.py on the NUMPY ORACLE (oracle/muscl_oracle.py), not the reference" if c.get("by_oracle") else
+                                    "oracle/make_named_fingerprints.py on the unmodified reference" + (" + HLLE 2-edit patch" if c.get("patch_hlle") else "")))
     t0 = time.time()
     for cp in c["checkpoints"]:
         target = 10**9 if cp < 0 else cp

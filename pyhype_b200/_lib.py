@@ -69,9 +69,6 @@ SIGNATURES = {
     "pyh_upload_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_commit_uploads": (C.c_int, [_vp]),
     "pyh_download_state_async": (C.c_int, [_vp, C.c_int, c_double_p]),
-    "pyh_stage_overlapped": (C.c_int, [_vp, C.c_int]),
-    "pyh_overlap_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    "pyh_unpack_halo_on": (C.c_int, [_vp, _vp, C.c_uint64]),
     "pyh_transfers_sync": (C.c_int, [_vp]),
     "pyh_downloads_sync": (C.c_int, [_vp]),
     "pyh_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -103,6 +100,7 @@ SIGNATURES = {
     "pyh_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pyh_residual": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_debug_fetch": (C.c_int, [_vp, C.c_int, C.c_int, c_double_p]),
+    "pyh_march_shape": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pyh_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "pyh_stream": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pyh_sync": (C.c_int, [_vp]),

@@ -18,7 +18,13 @@ SIDES = ("E", "W", "N", "S")
 class DeviceBackedState(ConservativeState):
     """``block.state``: a ConservativeState whose ``data`` is synchronised with the device copy
     on demand -- downloaded when the device is newer, re-uploaded before the next device call
-    whenever host code may have written to it (a getter hands out a writable array)."""
+    whenever host code may have written to it (a getter hands out a writable array).
+
+    Contract (differs from the reference, where ``state.data`` IS the solution): every READ of ``.data`` hands out the
+    current host array and marks it as possibly modified, so it is uploaded again before the next device call; an array
+    obtained earlier and kept across a device call (``a = block.state.data; solver.step(); a[...] = 0``) is a stale copy
+    -- the write is not seen by the device and the next read of ``.data`` returns a fresh download.  Re-read ``.data``
+    after every solver call, or assign through the setter (``block.state.data = array``), which always takes effect."""
 
     def __init__(self, fluid, shape, sync):
         self._sync = sync

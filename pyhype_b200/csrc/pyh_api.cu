@@ -42,7 +42,6 @@ static int set_err(int code, const char* fmt, ...) {
 
 // The stage kernel is instantiated per (flux, limiter, reconstruction, quadrature points) in three translation
 // units (pyh_march_nq{1,2,3}.cu, compiled in parallel); each exports its picker.
-typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const int, const unsigned long long);
 namespace pyh {
 MarchFn pick_march_nq1(int f, int l, int p);
 MarchFn pick_march_nq2(int f, int l, int p);
@@ -84,6 +83,7 @@ struct Ctx {
     long long dts_cap = 0;
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
     int march_nt = 128, march_tys = 64;
+    bool march_configured = false;   // cudaFuncSetAttribute done for this context's device
     // asynchronous state streaming (pyh_upload_state_async & co)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in_done = nullptr, ev_in_consumed = nullptr, ev_out_ready = nullptr;
@@ -91,16 +91,16 @@ struct Ctx {
     double* d_stage_in = nullptr;           // nblocks x (ny, nx, 4)
     double* d_stage_out = nullptr;
     std::vector<char> staged;
-    // overlap of the remote ghost exchange with the stage kernel (pyh_stage_overlapped)
-    bool overlap_capable = false;
+    // overlap of the remote strip exchange with the stage kernel: edge strips + exchange on s_edge, interior on `stream`
+    bool split_ns = false, split_ew = false;    // remote neighbours across north / south, east / west block edges
+    cudaStream_t s_edge = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_edge_done = nullptr;
     // pyh_run: one period of the time loop (1 step, or 2 for single-stage tableaux whose buffers alternate)
     // captured once as a CUDA graph and replayed
     cudaGraphExec_t run_graph = nullptr;
     int run_graph_steps = 0;
     int run_graph_i0 = 0;          // buffer holding the solution when the captured period starts
     long long run_graph_launches = 0;
-    unsigned long long halo_epoch_issued = 0;   // stamp handed to the latest pyh_unpack_halo_on
-    int n_remote_ctas = 0;
     Comm comm;                                  // multi-rank transport (pyh_comm_init); comm.comm == nullptr: single rank
 };
 
@@ -151,57 +151,90 @@ MarchFn pick_march(int f, int l, int p, int nq) {
     return nq == 1 ? pyh::pick_march_nq1(f, l, p) : (nq == 2 ? pyh::pick_march_nq2(f, l, p) : pyh::pick_march_nq3(f, l, p));
 }
 
-// lanes per CTA: two ring lanes per strip, so pick the width that wastes the fewest lanes for this nx
+// Strip shape of the stage kernel: nt lanes per thread block (nt - 4 output columns) x tys rows.
+// A thread block's run time is ~ (tys + 1) row times (one extra row of gradients / limiter in the prologue), and a row
+// time (~8 us) hardly depends on how many of the SM's 16 warp slots are taken -- the kernel is latency-bound per warp.  So
+// a launch costs about  waves x (tys + 1)  row times, waves = ceil(thread blocks / resident slots).  Large problems (many
+// waves) keep the measured optimum nt = widest, tys = 64 (profiles/r01j_tuning_notes.md); problems of a few waves or less
+// -- the reference's own examples: explosion_multi is 8 x 150^2, DMR 4 x 500^2 -- search (nt, tys) for the cheapest shape,
+// which above all avoids a sparsely filled second wave (DMR: 2 waves x 13 rows -> 1 wave x 18).
 void choose_march_shape(Ctx* c) {
+    const int nx = c->lay.nx, ny = c->lay.ny;
+    const long long nblk = (long long)std::max<size_t>(c->blocks.size(), 1);
+    const int nq = c->cfg.num_quadrature_points;
+    MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon, nq);
+    cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * MARCH_MAX_THREADS * (int)sizeof(double));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+    auto slots_for = [&](int n) -> long long {
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, n, (size_t)march_smem_doubles(nq) * n * sizeof(double));
+        if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = std::max(1, 512 / n); }
+        return (long long)occ * sms;
+    };
+    // default: the width that wastes the fewest lanes for this nx, 64 rows (capped so that there are thread blocks for ~6 waves)
     const int cand[] = {64, 96, 128, 160, 192};
     double best = -1.0;
     int nt = 128;
     for (int n : cand) {
         if (n > MARCH_MAX_THREADS) continue;
-        int strips = (c->lay.nx + n - 5) / (n - 4);
-        double util = (double)c->lay.nx / ((double)strips * n);
+        int strips = (nx + n - 5) / (n - 4);
+        double util = (double)nx / ((double)strips * n);
         if (util > best + 1e-9 || (util > best - 1e-9 && n > nt)) { best = util; nt = n; }
     }
-    if (const char* e = getenv("PYH_MARCH_NT")) { int v = atoi(e); if (v >= 32 && v <= MARCH_MAX_THREADS && v % 32 == 0) nt = v; }
-    c->march_nt = nt;
     int tys = 64;
+    {
+        long long nsx = (nx + nt - 5) / (nt - 4);
+        long long per_row_strip = nsx * nblk;
+        long long want_nsy = (sms * 6 + per_row_strip - 1) / per_row_strip;
+        if (want_nsy < 1) want_nsy = 1;
+        int cap = (int)((ny + want_nsy - 1) / want_nsy);
+        tys = std::max(4, std::min(tys, cap));
+    }
+    auto n_ctas = [&](int n, int ty) { return (long long)((nx + n - 5) / (n - 4)) * nblk * ((ny + ty - 1) / ty); };
+    if (n_ctas(nt, tys) <= 3 * slots_for(nt)) {   // small problem: cheapest (nt, tys) by the wave model
+        double best_cost = 1e300;
+        for (int n : cand) {
+            if (n > MARCH_MAX_THREADS) continue;
+            const long long slots = slots_for(n);
+            for (int ty = 2; ty <= std::min(ny, 128); ++ty) {
+                const long long ctas = n_ctas(n, ty);
+                const long long waves = (ctas + slots - 1) / slots;
+                const int last = ny - ((ny + ty - 1) / ty - 1) * ty;          // rows of the last (shortest) strip: ragged strips idle lanes
+                const double cost = (double)waves * (ty + 1.05) + 1e-3 * (ty - last) + 1e-4 * (128 - n);
+                if (cost < best_cost) { best_cost = cost; nt = n; tys = ty; }
+            }
+        }
+    }
+    if (const char* e = getenv("PYH_MARCH_NT")) { int v = atoi(e); if (v >= 32 && v <= MARCH_MAX_THREADS && v % 32 == 0) nt = v; }
     if (const char* e = getenv("PYH_MARCH_TYS")) { int v = atoi(e); if (v >= 1) tys = v; }
-    // enough CTAs to fill 148 SMs a few times over
-    long long nsx = (c->lay.nx + nt - 5) / (nt - 4);
-    long long per_row_strip = nsx * (long long)std::max<size_t>(c->blocks.size(), 1);
-    long long want_nsy = (148 * 6 + per_row_strip - 1) / per_row_strip;
-    if (want_nsy < 1) want_nsy = 1;
-    int cap = (int)((c->lay.ny + want_nsy - 1) / want_nsy);
-    tys = std::max(4, std::min(tys, cap));
+    c->march_nt = nt;
     c->march_tys = tys;
 }
 
-int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, bool overlapped = false) {
-    if (c->blocks.empty()) return 0;   // a rank without blocks only takes part in the reductions (blocks/base.py:473-513 allows it)
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, const TileLaunch& tl, cudaStream_t st) {
+    if (c->blocks.empty() || tl.gx == 0 || tl.gy == 0) return 0;   // a rank without blocks only takes part in the reductions (blocks/base.py:473-513 allows it)
     const int nq = c->cfg.num_quadrature_points;
     MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon, nq);
-    const int nt = c->march_nt, tys = c->march_tys;
+    const int nt = c->march_nt;
     size_t smem = (size_t)march_smem_doubles(nq) * nt * sizeof(double);
-    static thread_local MarchFn configured[64];
-    static thread_local int nconf = 0;
-    bool done = false;
-    for (int i = 0; i < nconf; ++i) if (configured[i] == fn) done = true;
-    if (!done) {
+    if (!c->march_configured) {   // per context = per device (the attribute is a per-device property of the function)
         CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * MARCH_MAX_THREADS * (int)sizeof(double)));
         if (const char* e = getenv("PYH_CARVEOUT")) CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-        if (nconf < 64) configured[nconf++] = fn;
+        c->march_configured = true;
     }
-    dim3 grid(cdiv(c->lay.nx, nt - 4), cdiv(c->lay.ny, tys), (unsigned)c->blocks.size());
-    static const bool no_wait = getenv("PYH_NO_EPOCH_WAIT") != nullptr;   // diagnostics
-    if (overlapped) {
-        dim3 g2(grid.x, grid.z, grid.y);   // row strips slowest, edge strips last (see the kernel)
-        fn<<<g2, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, 1, no_wait ? 0ull : c->halo_epoch_issued);
-    } else {
-        fn<<<grid, nt, smem, c->stream>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->C, tys, want_grad_dbg, 0, 0ull);
-    }
+    dim3 grid(tl.gx, tl.gy, (unsigned)c->blocks.size());
+    fn<<<grid, nt, smem, st>>>(c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C, tl.tys, want_grad_dbg, tl.tiles);
     CU(cudaGetLastError());
     c->launches++;
     return 0;
+}
+
+// the whole block in one launch
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
+    TileLaunch tl[3];
+    plan_tiles(c->lay.nx, c->lay.ny, c->march_nt, c->march_tys, false, false, tl);
+    return launch_stage(c, plan, want_grad_dbg, tl[0], c->stream);
 }
 
 // RK partial-sum plan for stage s (explicit_runge_kutta.py:63-75 restated as running sums:
@@ -220,19 +253,24 @@ int do_ghost(Ctx* c, int buf) {
     return 0;
 }
 
-int do_stage(Ctx* c, int s, bool overlapped = false) {
+// buffer roles of stage s: returns the plan, advances c->cur (and the solution role after the last stage)
+StagePlan advance_roles(Ctx* c, int s, bool fuse_dt = false) {
     const int S = c->cfg.num_stages;
     int cur = (s == 0) ? c->i0 : c->cur;
     const int next = plan_next_buffer(S, s, cur, c->i0, c->i1, c->i2);
     StagePlan p = make_plan(c, s, cur, next);
-    int rc = launch_stage(c, p, 0, overlapped);
-    if (rc) return rc;
+    p.fuse_dt = (fuse_dt && s == S - 1) ? 1 : 0;   // the last stage also reduces the CFL minimum of the state it writes
     c->cur = next;
     if (s == S - 1) {
         if (S == 1) std::swap(c->i0, c->i1);
         c->cur = c->i0;
     }
-    return 0;
+    return p;
+}
+
+int do_stage(Ctx* c, int s) {
+    StagePlan p = advance_roles(c, s);
+    return launch_stage(c, p, 0);
 }
 
 int set_active(Ctx* c, int active) {
@@ -252,22 +290,51 @@ int launch_dt(Ctx* c, int buf, int respect_active = 0) {
 // Remote ghost strips of buffer `buf` (GhostBlock.send_boundary_data / recieve_boundary_data / apply_recv_buffers_to_state,
 // blocks/ghost.py:169-241, and the Waitall of blocks/base.py:454-465): pack the edge strips the neighbour ranks need, ONE
 // grouped ncclSend / ncclRecv batch, unpack into the ghost frames -- all in order on the compute stream (capturable).
-int exchange_halo(Ctx* c, int buf) {
+int exchange_halo(Ctx* c, int buf, cudaStream_t st = nullptr) {
     Comm& m = c->comm;
+    if (!st) st = c->stream;
     if (!m.comm || c->slots.empty()) return 0;
     NcclApi& N = nccl_api();
     const int mx = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(mx, 128), (unsigned)c->slots.size());
-    k_pack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_send);
+    k_pack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_send);
     CU(cudaGetLastError());
     NC(N.GroupStart());
-    for (const HaloMsg& r : m.recvs) NC(N.Recv(m.d_recv + r.offset, (size_t)r.len, kNcclFloat64, r.peer, m.comm, c->stream));
-    for (const HaloMsg& q : m.sends) NC(N.Send(m.d_send + q.offset, (size_t)q.len, kNcclFloat64, q.peer, m.comm, c->stream));
+    for (const HaloMsg& r : m.recvs) NC(N.Recv(m.d_recv + r.offset, (size_t)r.len, kNcclFloat64, r.peer, m.comm, st));
+    for (const HaloMsg& q : m.sends) NC(N.Send(m.d_send + q.offset, (size_t)q.len, kNcclFloat64, q.peer, m.comm, st));
     NC(N.GroupEnd());
-    k_unpack_halo<<<grid, 128, 0, c->stream>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_recv);
+    k_unpack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_recv);
     CU(cudaGetLastError());
     c->launches += 2;
     return 0;
+}
+
+// One Runge-Kutta stage and the ghost refresh behind it (ExplicitRungeKutta.integrate's loop body, explicit_runge_kutta.py:63-80:
+// residual + update, then Blocks.apply_boundary_condition).  With remote neighbours the stage is split (pyh_plan.cuh: plan_tiles):
+// the thin strips that produce the cells other ranks need run first on a side stream, followed there by pack -> grouped
+// ncclSend / ncclRecv -> unpack, while the interior launch runs on the compute stream; the two streams join before the local
+// ghost copies.  The exchange is thereby off the critical path and a rank may run up to one stage ahead of its neighbours.
+int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
+    static const bool no_overlap = getenv("PYH_NO_HALO_OVERLAP") != nullptr;   // diagnostics: blocking exchange behind one launch
+    StagePlan p = advance_roles(c, s, fuse_dt);
+    int rc;
+    if (!c->comm.comm || c->slots.empty() || no_overlap || !c->s_edge) {
+        if ((rc = launch_stage(c, p, 0))) return rc;
+        if ((rc = exchange_halo(c, c->cur))) return rc;
+        return do_ghost(c, c->cur);
+    }
+    TileLaunch tl[3];
+    const int n = plan_tiles(c->lay.nx, c->lay.ny, c->march_nt, c->march_tys, c->split_ns, c->split_ew, tl);
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->s_edge, c->ev_fork, 0));
+    for (int q = 0; q < n; ++q)
+        if (tl[q].edge && (rc = launch_stage(c, p, 0, tl[q], c->s_edge))) return rc;
+    if ((rc = exchange_halo(c, c->cur, c->s_edge))) return rc;
+    CU(cudaEventRecord(c->ev_edge_done, c->s_edge));
+    for (int q = 0; q < n; ++q)
+        if (!tl[q].edge && (rc = launch_stage(c, p, 0, tl[q], c->stream))) return rc;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_edge_done, 0));
+    return do_ghost(c, c->cur);
 }
 
 // Global CFL minimum and realizability flag (Solver.get_dt gathers and broadcasts the minimum, solvers/base.py:128-131;
@@ -470,22 +537,6 @@ int pyh_finalize(void* ctx) {
         CU(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(HaloSlot), cudaMemcpyHostToDevice));
     }
     choose_march_shape(c);
-    if (!c->slots.empty()) {   // thread blocks per launch that read remotely owned ghost cells (pyh_overlap_info)
-        const int nt = c->march_nt, tys = c->march_tys, nx = c->lay.nx, ny = c->lay.ny;
-        const unsigned gx = cdiv(nx, nt - 4), gy = cdiv(ny, tys), gz = (unsigned)c->blocks.size();
-        int n = 0;
-        for (unsigned z = 0; z < gz; ++z)
-            for (unsigned y = 0; y < gy; ++y)
-                for (unsigned x = 0; x < gx; ++x) {
-                    const BlkDev& D = c->blocks[z].dev;
-                    const int jhi = (int)x * (nt - 4) - 3 + nt;
-                    const int ihi = std::min((int)y * tys + tys, ny) + 1;
-                    n += ((x == 0 && D.remote_slot[PYH_WEST] >= 0) || (jhi >= nx && D.remote_slot[PYH_EAST] >= 0) ||
-                          (y == 0 && D.remote_slot[PYH_SOUTH] >= 0) || (ihi >= ny && D.remote_slot[PYH_NORTH] >= 0)) ? 1 : 0;
-                }
-        c->n_remote_ctas = n;
-        c->overlap_capable = gz <= 65535 && gy <= 65535;
-    }
     c->finalized = true;
     return 0;
 }
@@ -514,6 +565,9 @@ int pyh_destroy(void* ctx) {
     for (cudaEvent_t e : c->ev_out_done) if (e) cudaEventDestroy(e);
     if (c->run_graph) cudaGraphExecDestroy(c->run_graph);
     if (c->comm.comm) nccl_api().CommDestroy(c->comm.comm);
+    if (c->s_edge) { cudaStreamSynchronize(c->s_edge); cudaStreamDestroy(c->s_edge); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_edge_done) cudaEventDestroy(c->ev_edge_done);
     if (c->comm.d_send) cudaFree(c->comm.d_send);
     if (c->comm.d_recv) cudaFree(c->comm.d_recv);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
@@ -803,53 +857,14 @@ int pyh_stage(void* ctx, int stage) {
     return 0;
 }
 
-int pyh_stage_overlapped(void* ctx, int stage) {
-    Ctx* c = as_ctx(ctx);
-    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
-    if (stage != c->stage_next || stage >= c->cfg.num_stages) return set_err(PYH_ERR_STATE, "stage %d out of order (expected %d)", stage, c->stage_next);
-    if (!c->overlap_capable) return set_err(PYH_ERR_STATE, "pyh_stage_overlapped: context has no remote edges");
-    CU(cudaSetDevice(c->cfg.device));
-    int rc = do_stage(c, stage, true);
-    if (rc) return rc;
-    c->stage_next = stage + 1;
-    return 0;
-}
-
-int pyh_unpack_halo_on(void* ctx, const double* dev_recv, uint64_t stream) {
-    Ctx* c = as_ctx(ctx);
-    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
-    if (c->slots.empty()) return 0;
-    CU(cudaSetDevice(c->cfg.device));
-    cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
-    int m = std::max(c->lay.nx, c->lay.ny);
-    dim3 grid(cdiv(m, 128), (unsigned)c->slots.size());
-    k_unpack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[c->cur], c->d_slots, dev_recv);
-    CU(cudaGetLastError());
-    k_set_halo_epoch<<<1, 1, 0, st>>>(c->d_ctl, ++c->halo_epoch_issued);
-    CU(cudaGetLastError());
-    c->launches += 2;
-    return 0;
-}
-
-int pyh_overlap_info(void* ctx, int32_t* capable, int32_t* n_remote_ctas) {
-    Ctx* c = as_ctx(ctx);
-    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
-    if (capable) *capable = c->overlap_capable ? 1 : 0;
-    if (n_remote_ctas) *n_remote_ctas = c->n_remote_ctas;
-    return 0;
-}
-
 int pyh_step(void* ctx, double dt) {
     Ctx* c = as_ctx(ctx);
     if (c && !c->slots.empty() && !c->comm.comm)
         return set_err(PYH_ERR_STATE, "pyh_step on a context with remote neighbours and no pyh_comm_init; drive the stages from the host");
     int rc = pyh_step_begin(ctx, dt);
     if (rc) return rc;
-    for (int s = 0; s < c->cfg.num_stages; ++s) {
-        if ((rc = do_stage(c, s))) return rc;
-        if ((rc = exchange_halo(c, c->cur))) return rc;
-        if ((rc = do_ghost(c, c->cur))) return rc;
-    }
+    for (int s = 0; s < c->cfg.num_stages; ++s)
+        if ((rc = stage_and_refresh(c, s))) return rc;
     c->stage_next = c->cfg.num_stages;
     return 0;
 }
@@ -879,23 +894,24 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     h.dts = ddts; h.dts_cap = ddts ? dts_cap : 0;
     CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     int rc;
-    // one time step: CFL reduction, dt, stages + ghost refresh, t += dt; every kernel early-exits once t >= t_final
+    // one time step: [all-reduce of] the CFL minimum, dt, stages + ghost refresh, t += dt; every kernel early-exits once
+    // t >= t_final.  The CFL minimum and the realizability flag of a step's FINAL state are reduced inside its last stage
+    // (plan.fuse_dt: the state is still in registers there), so only the first step of a call needs the k_dt pass below.
+    static const bool no_fuse = getenv("PYH_NO_FUSED_DT") != nullptr;   // diagnostics: k_dt as a kernel of its own every step
     auto enqueue_step = [&]() -> int {
         int r;
-        if ((r = launch_dt(c, c->i0, 1))) return r;
+        if (no_fuse && (r = launch_dt(c, c->i0, 1))) return r;
         if ((r = reduce_dt(c))) return r;
         k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 0, nullptr);
         CU(cudaGetLastError());
-        for (int s = 0; s < c->cfg.num_stages; ++s) {
-            if ((r = do_stage(c, s))) return r;
-            if ((r = exchange_halo(c, c->cur))) return r;
-            if ((r = do_ghost(c, c->cur))) return r;
-        }
+        for (int s = 0; s < c->cfg.num_stages; ++s)
+            if ((r = stage_and_refresh(c, s, !no_fuse))) return r;
         k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl);
         CU(cudaGetLastError());
         c->launches += 2;
         return 0;
     };
+    if (!no_fuse && (rc = launch_dt(c, c->i0, 0))) return rc;   // CFL minimum of the state the call starts from
     static const bool no_graph = getenv("PYH_NO_GRAPH") != nullptr;
     int64_t enqueued = 0;          // steps handed to the stream in this call (>= steps the device executes)
     const int period = (c->cfg.num_stages == 1) ? 2 : 1;   // steps after which the buffer roles repeat
@@ -948,8 +964,8 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         CU(cudaStreamSynchronize(c->stream));
         if ((enqueued - (int64_t)h.nsteps) & 1) { std::swap(c->i0, c->i1); c->cur = c->i0; }
     }
-    // final realizability check of the last state (Euler2D.py:204)
-    if ((rc = launch_dt(c, c->i0))) return rc;
+    // final realizability check of the last state (Euler2D.py:204): its flag was reduced by the last executed step
+    if (no_fuse && (rc = launch_dt(c, c->i0))) return rc;
     if ((rc = reduce_dt(c))) return rc;
     k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, c->d_tmp);
     CU(cudaGetLastError());
@@ -1090,6 +1106,17 @@ int pyh_comm_init(void* ctx, int32_t rank, int32_t world, const void* id, const 
         m.sends.push_back(HaloMsg{peer, c->blocks[hs.blk].d.gid, hs.side, hs.offset, len});
         m.recvs.push_back(HaloMsg{peer, ng, opposite[hs.side], hs.offset, len});
     }
+    for (const HaloSlot& hs : c->slots) {
+        if (hs.side == PYH_NORTH || hs.side == PYH_SOUTH) c->split_ns = true;
+        else c->split_ew = true;
+    }
+    if (!c->slots.empty() && !c->s_edge) {
+        int lo = 0, hi = 0;   // edge strips + exchange win the first free thread-block slots
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->s_edge, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_edge_done, cudaEventDisableTiming));
+    }
     std::sort(m.sends.begin(), m.sends.end(), msg_less);
     std::sort(m.recvs.begin(), m.recvs.end(), msg_less);
     m.doubles = c->halo_doubles;
@@ -1112,6 +1139,14 @@ int pyh_comm_info(void* ctx, int32_t* rank, int32_t* world, int32_t* n_msgs, int
     if (world) *world = c->comm.comm ? c->comm.world : 1;
     if (n_msgs) *n_msgs = (int32_t)c->comm.sends.size();
     if (doubles_per_exchange) *doubles_per_exchange = c->comm.doubles;
+    return 0;
+}
+
+int pyh_march_shape(void* ctx, int32_t* lanes, int32_t* rows) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (lanes) *lanes = c->march_nt;
+    if (rows) *rows = c->march_tys;
     return 0;
 }
 

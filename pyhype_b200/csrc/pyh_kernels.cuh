@@ -95,24 +95,9 @@ k_unpack_halo(const BlkDev* __restrict__ blks, Layout lay, unsigned buf, const H
     dst[o] = d[0]; dst[o + lay.plane] = d[1]; dst[o + 2 * lay.plane] = d[2]; dst[o + 3 * lay.plane] = d[3];
 }
 
-__global__ void k_set_halo_epoch(Control* ctl, unsigned long long epoch) {
-    __threadfence();
-    *(volatile unsigned long long*)&ctl->halo_epoch = epoch;
-}
-
 // ------------------------------------------------------------------------------------------------
 // CFL reduction + realizability (quad_block.py:423-436, states/conservative.py:161-165)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long dkey(double x) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dunkey(unsigned long long k) {
-    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
-constexpr unsigned long long DKEY_INF = 0xfff0000000000000ull;  // dkey(+inf)
-
 constexpr int DT_ROWS = 16;
 
 __global__ void __launch_bounds__(256)

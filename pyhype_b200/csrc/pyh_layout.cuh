@@ -48,6 +48,7 @@ struct RkTarget {
 struct StagePlan {
     int ntargets;
     int write_residual;   // test hook: also store R itself into BlkDev::dbg
+    int fuse_dt;          // last stage of a step inside pyh_run: CFL minimum + realizability of the NEW state (the next step's dt)
     unsigned cur;         // slab offset of the state buffer this stage reads
     RkTarget t[PYH_MAX_STAGES];
 };
@@ -63,10 +64,21 @@ struct Control {
     int active;      // 1 while t < t_final
     int bad;         // unrealizable state seen
     int pad[2];
-    unsigned long long halo_epoch;   // stamp of the last remote ghost exchange that has landed (pyh_unpack_halo_on)
     double* dts;                     // pyh_run: optional per-step dt record (device), dts_cap entries
     long long dts_cap;
 };
+
+// doubles as order-preserving 64-bit keys (atomicMin on the CFL minimum; ncclAllReduce(min, uint64) across ranks)
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+constexpr unsigned long long DKEY_INF = 0xfff0000000000000ull;  // dkey(+inf)
+
 
 struct BlkDev {
     double* base;                 // the block's slab

@@ -3,7 +3,6 @@
 #include "pyh_stage_march.cuh"
 
 namespace pyh {
-typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int, const int, const unsigned long long);
 template <int F, int L>
 static MarchFn mpick_p(int p) { return p ? k_stage_march<F, L, 1, 3> : k_stage_march<F, L, 0, 3>; }
 template <int F>

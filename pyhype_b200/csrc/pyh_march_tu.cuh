@@ -11,8 +11,21 @@ namespace pyh {
 #define PYH_MARCH_MINB 4
 #endif
 constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
+
+// Which strips of every block one launch of the stage kernel covers.  A plain launch covers the whole block; a context with remote
+// neighbours splits every stage into an EDGE launch (the thin strips that produce the cells other ranks need) and an INTERIOR
+// launch, so that the strip exchange runs behind the interior (pyh_api.cu: stage_and_refresh).
+struct MarchTiles {
+    int row0, rowstride, row1;   // row strip blockIdx.y covers rows [row0 + y * rowstride, min(that + tys, row1))
+    int xfirst, xstride;         // column strip = xfirst + blockIdx.x * xstride
+};
+struct BlkDev;
+struct Control;
+typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, Control*, const Consts, const int, const int, const MarchTiles);
 // shared-memory doubles per thread for NQ quadrature points per face:
 // sQ[3][4], sFE[2][NQ][4], sIW[2][4], sQN[2][NQ][4], sIS[4], sQW[NQ][4], sQS[NQ][4]
+// (48 doubles per thread for NQ = 1: 4 thread blocks of 128 threads are exactly the 196 KB shared-memory carve-out, which
+// leaves 60 KB of L1; ONE more double per thread selects the 228 KB carve-out and costs 10 % -- measured, profiles/r02b)
 constexpr int march_smem_doubles(int nq) { return 24 + 24 * nq; }
 // resident CTAs per SM the launch bounds ask for (shared memory is the limiter for NQ > 1)
 constexpr int march_min_blocks(int nq) { return nq == 1 ? PYH_MARCH_MINB : (nq == 2 ? 3 : 2); }

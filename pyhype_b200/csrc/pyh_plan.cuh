@@ -9,6 +9,7 @@
 #pragma once
 #include <string.h>
 #include "pyh_layout.cuh"
+#include "pyh_march_tu.cuh"
 
 namespace pyh {
 
@@ -63,6 +64,48 @@ inline StagePlan plan_stage(const double* a, int S, const PlaneOffsets& po, int 
         p.t[p.ntargets++] = t;
     }
     return p;
+}
+
+// ---- which strips each launch of one stage covers ------------------------------------------------------------------
+struct TileLaunch {
+    MarchTiles tiles;
+    unsigned gx, gy;   // grid.x, grid.y (grid.z = number of local blocks)
+    int tys;           // rows per strip of this launch
+    int edge;          // 1: produces cells that remote neighbours need (runs ahead of the strip exchange)
+};
+
+// A context without remote neighbours (split_ns == split_ew == false) covers every block with ONE launch of
+// ceil(nx / (nt - 4)) x ceil(ny / tys) strips.  With remote neighbours across north / south edges the first and the last
+// `th` rows of every block go into an edge launch of thin strips, with remote neighbours across east / west edges so do the
+// first and the last column strip of the remaining rows; the interior launch takes the rest.  The launches of one stage
+// write disjoint cells and all read the same input buffer, so they may run concurrently and in any order; together they
+// cover every cell exactly once (tests/test_kernel_twin.py runs the split on the CPU).  Returns the number of launches.
+constexpr int kEdgeRows = 4;
+inline int plan_tiles(int nx, int ny, int nt, int tys, bool split_ns, bool split_ew, TileLaunch out[3]) {
+    const int nsx = (nx + nt - 5) / (nt - 4);
+    int n = 0;
+    const int th = kEdgeRows;
+    if (split_ns && ny < 2 * th + 1) split_ns = false;   // tiny blocks: nothing left to overlap with
+    const int mid0 = split_ns ? th : 0, mid1 = split_ns ? ny - th : ny;
+    if (split_ew && nsx < 3) split_ew = false;           // the two edge column strips would be the whole block
+    if (split_ns) {       // rows [0, th) and [ny - th, ny), every column strip
+        TileLaunch t;
+        t.tiles = MarchTiles{0, ny - th, ny, 0, 1};
+        t.gx = (unsigned)nsx; t.gy = 2; t.edge = 1; t.tys = th;
+        out[n++] = t;
+    }
+    const int gy_mid = (mid1 - mid0 + tys - 1) / tys;
+    if (split_ew) {       // column strips 0 and nsx - 1 of the middle rows
+        TileLaunch t;
+        t.tiles = MarchTiles{mid0, tys, mid1, 0, nsx - 1};
+        t.gx = 2; t.gy = (unsigned)gy_mid; t.edge = 1; t.tys = tys;
+        out[n++] = t;
+    }
+    TileLaunch t;         // the rest
+    t.tiles = MarchTiles{mid0, tys, mid1, split_ew ? 1 : 0, 1};
+    t.gx = (unsigned)(split_ew ? nsx - 2 : nsx); t.gy = (unsigned)gy_mid; t.edge = (split_ns || split_ew) ? 0 : 1; t.tys = tys;
+    out[n++] = t;
+    return n;
 }
 
 }  // namespace pyh

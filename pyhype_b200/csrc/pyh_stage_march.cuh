@@ -4,7 +4,7 @@
 // limiters/base.py + limiters/limiters.py, gradients/greengauss.py, blocks/quad_block.py:120-218,
 // time_marching/explicit_runge_kutta.py:63-89 -- one launch per RK stage for ALL local blocks.
 //
-// Work decomposition.  grid = (column strips, row strips, blocks).  A CTA of NT threads owns NT-4
+// Work decomposition.  grid = (column strips, row strips, blocks) of the strips `tiles` selects.  A CTA of NT threads owns NT-4
 // output columns and `tys` rows of one block; thread t <-> column j = strip_origin - 2 + t and
 // marches south -> north.  Lane roles: 0 and NT-1 only publish their column's reconstruction
 // variables; 1 and NT-2 additionally evaluate gradient + limiter (their face states are the outer
@@ -33,72 +33,31 @@
 
 namespace pyh {
 
-#ifndef PYH_PAIR_BARRIER
-#define PYH_PAIR_BARRIER 0
-#endif
-// unroll factors of the two per-variable loops of phase B (1 = rolled: the register file only holds one variable's working
-// set; 2 and 4 still compile to <= 128 registers without spills and give the scheduler two / four variables' division
-// chains to interleave -- knobs for tools/build_variant.sh, not yet measured)
-#ifndef PYH_UNROLL_B1
-#define PYH_UNROLL_B1 1
-#endif
-#ifndef PYH_UNROLL_B2
-#define PYH_UNROLL_B2 1
-#endif
-constexpr int kUnrollB1 = PYH_UNROLL_B1, kUnrollB2 = PYH_UNROLL_B2;   // (#pragma unroll does not expand macros)
+// Build-time switches that remain (the round-1 tuning knobs were measured on the B200 in round 2, profiles/r02a_variants_ab.txt
+// and r02b_variants_combined.txt: the winners are now the only code path, the losers are gone):
+//   PYH_SKIP_UNIT_ROT (1): skip the rotation by theta == 0 on blocks whose vertical faces are all axis-aligned.
 #ifndef PYH_SKIP_UNIT_ROT
 #define PYH_SKIP_UNIT_ROT 1
 #endif
-// PYH_D_EARLY (default 0, to be measured): phase D waits on its Runge-Kutta source loads right where it issues them (47 % of
-// its samples are long_scoreboard, profiles/r01s_summary.md).  1: issue the area and the source loads of the first two
-// targets at the top of D, ahead of the residual arithmetic; 2: ahead of the south-face Riemann solve.
-#ifndef PYH_D_EARLY
-#define PYH_D_EARLY 0
-#endif
-// PYH_B_GEOM_FIRST (default 0, to be measured): the 13 + 8 NQ geometry loads of phase B are issued at the very top of the
-// row iteration, ahead of the ring bookkeeping (publish row r+1, issue the state loads of row r+2: ~150 instructions that
-// need no geometry), instead of right in front of their first consumer, where 10 % of all warp samples wait on them
-// (profiles/r01s_summary.md).  Nothing but the loop-carried state is live at that point, so the registers are there.
-#ifndef PYH_B_GEOM_FIRST
-#define PYH_B_GEOM_FIRST 0
-#endif
-// PYH_MINMAX_NET (default 0, to be measured): 5-point maximum and minimum of the limiter through a small sorting network
-// (6 FP64 comparisons per variable instead of 8; same values for every finite input)
-#ifndef PYH_MINMAX_NET
-#define PYH_MINMAX_NET 0
-#endif
+constexpr int kUnrollB2 = 2;   // two variables' limiter chains in flight (8 division chains): -0.9 % measured; 4 was slower
 
-// PYH_COLD_HOOKS (default 0, to be measured): the test hooks of the kernel (gradient / limiter / residual stores for
-// pyh_debug_fetch and pyh_residual) are small enough for the compiler to predicate, so their address arithmetic is issued
-// for every cell even though the predicate is false in production (~85 of 2612 warp instructions per cell, profiles/
-// r01s_summary.md).  With the flag they sit behind a call to an out-of-line function.
-#ifndef PYH_COLD_HOOKS
-#define PYH_COLD_HOOKS 0
-#endif
-#if PYH_COLD_HOOKS
+// the test hooks of the kernel (gradient / limiter / residual stores for pyh_debug_fetch and pyh_residual) sit behind calls to
+// out-of-line functions, so that their address arithmetic is not issued (predicated off) for every cell in production
 static __device__ __noinline__ void hook_store2(double* p, size_t i0, double v0, size_t i1, double v1) { p[i0] = v0; p[i1] = v1; }
 static __device__ __noinline__ void hook_store1(double* p, size_t i0, double v0) { p[i0] = v0; }
 static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t stride, double v0, double v1, double v2, double v3) {
     p[i0] = v0; p[i0 + stride] = v1; p[i0 + 2 * stride] = v2; p[i0 + 3 * stride] = v3;
 }
-#endif
 
-// PYH_LDG (default 0, to be measured): state and geometry loads through ld.global.nc (LDG.E.CONSTANT) instead of the generic
-// LD the compiler emits for pointers fetched from the block table; both planes are read-only for the lifetime of a launch
-#ifndef PYH_LDG
-#define PYH_LDG 0
-#endif
-#if PYH_LDG && !defined(PYH_HOST_TWIN)
+// state and geometry are read-only for the lifetime of a launch (the stage writes other buffers; the ghost frame of its input
+// was completed by earlier kernels): ld.global.nc (LDG.E.CONSTANT) instead of the generic LD the compiler emits for pointers
+// fetched from the block table
+#if !defined(PYH_HOST_TWIN)
 #define PYH_RO(expr) __ldg(&(expr))
 #else
 #define PYH_RO(expr) (expr)
 #endif
-// level 2: the stage's input state as well (NOT with pyh_stage_overlapped: its remote ghost cells land during the launch)
-#if PYH_LDG >= 2 && !defined(PYH_HOST_TWIN)
-#define PYH_ROS(expr) __ldg(&(expr))
-#else
-#define PYH_ROS(expr) (expr)
-#endif
+#define PYH_ROS(expr) PYH_RO(expr)
 
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
@@ -106,32 +65,13 @@ typedef std::integral_constant<bool, false> SafeTag;
 template <int FLUX, int LIM, int PRIM, int NQ>
 __global__ void __launch_bounds__(MARCH_MAX_THREADS, march_min_blocks(NQ))
 k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-              const Control* __restrict__ ctl, const Consts C, const int tys, const int want_grad_dbg,
-              const int order_mode, const unsigned long long wait_epoch) {
+              const Control* __restrict__ ctl, Control* __restrict__ ctl_out, const Consts C, const int tys, const int want_grad_dbg,
+              const MarchTiles tiles) {
     if (!ctl->active) return;
-    // Block coordinates: (column strip, row strip, mesh block).  Plain launches: grid = (strips x, strips y, blocks).
-    // Overlapped launches (pyh_stage_overlapped): grid = (strips x, blocks, strips y) with the row-strip index
-    // rotated by one, i.e. row strips are the slowest dispatch dimension and the two that touch a block's south /
-    // north edge are dispatched LAST; by then the NCCL strip exchange running on the communication stream has
-    // normally landed.  Thread blocks that read remotely owned ghost cells wait for its epoch stamp.
-    const unsigned bx = blockIdx.x;
-    const unsigned by = order_mode ? (blockIdx.z + 1u) % gridDim.z : blockIdx.y;
-    const unsigned bz = order_mode ? blockIdx.y : blockIdx.z;
-    if (wait_epoch) {
-        const BlkDev& Bp = blks[bz];
-        const int jhi = (int)bx * ((int)blockDim.x - 4) - 3 + (int)blockDim.x;    // last column this thread block reads
-        const int ihi = min((int)by * tys + tys, lay.ny) + 1;                     // last row it reads
-        const bool touch = (bx == 0 && Bp.remote_slot[PYH_WEST] >= 0) || (jhi >= lay.nx && Bp.remote_slot[PYH_EAST] >= 0) ||
-                           (by == 0 && Bp.remote_slot[PYH_SOUTH] >= 0) || (ihi >= lay.ny && Bp.remote_slot[PYH_NORTH] >= 0);
-        if (touch) {
-            if (threadIdx.x == 0) {
-                const volatile unsigned long long* ep = &ctl->halo_epoch;
-                while (*ep < wait_epoch) __nanosleep(256);
-                __threadfence();
-            }
-            __syncthreads();
-        }
-    }
+    // Block coordinates: (column strip, row strip, mesh block); `tiles` selects the strips this launch covers (pyh_march_tu.cuh).
+    const unsigned bx = (unsigned)(tiles.xfirst + (int)blockIdx.x * tiles.xstride);
+    const unsigned by = blockIdx.y;
+    const unsigned bz = blockIdx.z;
 #ifdef PYH_HOST_TWIN
     extern double smem[];            // tests/host_twin: the emulator's per-block buffer
 #else
@@ -146,6 +86,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     double* const sIS = sQN + 8 * NQ * NT;         // [4][NT]
     double* const sQW = sIS + 4 * NT;              // [NQ][4][NT]  west-face states of (r, j), private
     double* const sQS = sQW + 4 * NQ * NT;         // [NQ][4][NT]  south-face states of (r, j), private
+    double dtmin = __longlong_as_double(0x7ff0000000000000ll);   // running CFL minimum of this thread's cells (plan.fuse_dt)
 
     auto iFE = [&](int par_, int q, int k, int tt) { return ((par_ * NQ + q) * 4 + k) * NT + tt; };   // also sQN
     auto iQW = [&](int q, int k) { return (q * 4 + k) * NT + t; };                                    // also sQS
@@ -159,8 +100,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
     const int j = (int)bx * (NT - 4) - 2 + t;
-    const int i0 = (int)by * tys;
-    const int i1 = min(i0 + tys, ny);
+    const int i0 = tiles.row0 + (int)by * tiles.rowstride;
+    const int i1 = min(i0 + tys, tiles.row1);
     const bool act = (j >= -1) && (j <= nx);
     const bool real = (j >= 0) && (j < nx);
     const bool doB = real && (t >= 1) && (t <= NT - 2);
@@ -219,25 +160,6 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
         const bool full = (r >= i0) && (r < i1);           // rows this strip outputs
         const unsigned o = (unsigned)((r + 1) * pitch + PADL + jc);
 
-#if PYH_B_GEOM_FIRST
-        double gLE = 0.0, gLW = 0.0, gLN = 0.0, gLS = 0.0, gcE = 0.0, gcW = 0.0, gcN = 0.0, gcS = 0.0, gsE = 0.0, gsW = 0.0, gsN = 0.0, gsS = 0.0, gA = 1.0;
-        double gdx[NQ][4], gdy[NQ][4];
-        if (doB && (r < ny)) {
-            const unsigned oE = o + 1, oN = o + pitch;
-            gLE = PYH_RO(G[po.Lv + oE]); gLW = PYH_RO(G[po.Lv + o]); gLN = PYH_RO(G[po.Lh + oN]); gLS = PYH_RO(G[po.Lh + o]);
-            gcE = PYH_RO(G[po.cv + oE]); gcW = PYH_RO(G[po.cv + o]); gcN = PYH_RO(G[po.ch + oN]); gcS = PYH_RO(G[po.ch + o]);
-            gsE = PYH_RO(G[po.sv + oE]); gsW = PYH_RO(G[po.sv + o]); gsN = PYH_RO(G[po.sh + oN]); gsS = PYH_RO(G[po.sh + o]);
-            gA = PYH_RO(G[po.A + o]);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    gdx[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2) * PL + o]);
-                    gdy[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o]);
-                }
-            }
-        }
-#endif
         // top: publish row r+1, issue the loads of row r+2 (L2 prefetch hints were measured and hurt: profiles/r01h_summary.md)
         to_recon(Qn);
         publish(sp, Qn);
@@ -252,20 +174,6 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             if (doB && rowreal) {
                 const unsigned oE = o + 1, oN = o + pitch;
                 // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155)
-#if PYH_B_GEOM_FIRST
-                (void)oE; (void)oN;
-                double LE = gLE, LW = gLW, LN = gLN, LS = gLS;
-#if PYH_FOLD_POW2
-                LE = 0.5 * LE; LW = 0.5 * LW; LN = 0.5 * LN; LS = 0.5 * LS;
-#endif
-                double xlE = LE * gcE, xlW = LW * (-gcW);
-                double xlN = LN * gcN, xlS = LS * (-gcS);
-                double ylE = LE * gsE, ylW = LW * (-gsW);
-                double ylN = LN * gsN, ylS = LS * (-gsS);
-                double Acell = gA;
-                double (&dx)[NQ][4] = gdx;
-                double (&dy)[NQ][4] = gdy;
-#else
                 double LE = PYH_RO(G[po.Lv + oE]), LW = PYH_RO(G[po.Lv + o]), LN = PYH_RO(G[po.Lh + oN]), LS = PYH_RO(G[po.Lh + o]);
 #if PYH_FOLD_POW2
                 // half face weights: (0.5 (q + qE)) * xlE == (q + qE) * (0.5 xlE), both scalings exact (pyh_math.cuh)
@@ -285,13 +193,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         dy[q][f] = PYH_RO(G[po.dxy + ((q * 4 + f) * 2 + 1) * PL + o]);
                     }
                 }
-#endif
                 bool okA = true;
                 double ia = Ar<true>::rcp(Acell, okA);
                 if (!okA) ia = 1.0 / Acell;
                 // pass 1: gradient and the high-order terms of the four faces (at every quadrature point); the
                 // terms wait in this thread's own face-state slots so that no geometry is live while the limiter divides
-#pragma unroll kUnrollB1
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
@@ -310,11 +217,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         sQN[iFE(par, p, k, t)] = gx * dx[p][2] + gy * dy[p][2];
                         sQS[iQW(p, k)] = gx * dx[p][3] + gy * dy[p][3];
                     }
-#if PYH_COLD_HOOKS
                     if (want_grad_dbg) { if (full && outcol) hook_store2(B.dbgG, k * (size_t)PL + o, gx, (4 + k) * (size_t)PL + o, gy); }
-#else
-                    if (want_grad_dbg && full && outcol) { B.dbgG[k * (size_t)PL + o] = gx; B.dbgG[(4 + k) * (size_t)PL + o] = gy; }
-#endif
                 }
                 // pass 2: SlopeLimiter._get_slope / _limit (limiters/base.py:47-108, 179-187), four faces side by side;
                 // phi is the minimum over every quadrature point of every face
@@ -323,17 +226,12 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     const double q = qc_[k * NT + t], qW = qc_[k * NT + t - 1], qE = qc_[k * NT + t + 1];
                     const double qS = qm_[k * NT + t], qN = qp_[k * NT + t];
                     double term[NQ][4];
-#if PYH_MINMAX_NET
                     // maximum and minimum of the five values with 6 instead of 8 FP64 comparisons: order the two neighbour
                     // pairs once (one comparison yields both the larger and the smaller), then reduce
                     const bool wge = qW > qE, sgn = qS > qN;
                     const double h1 = wge ? qW : qE, l1 = wge ? qE : qW, h2 = sgn ? qS : qN, l2 = sgn ? qN : qS;
                     double mx = dmax2(dmax2(h1, h2), q);
                     double mn = dmin2(dmin2(l1, l2), q);
-#else
-                    double mx = dmax2(dmax2(dmax2(dmax2(q, qW), qE), qS), qN);
-                    double mn = dmin2(dmin2(dmin2(dmin2(q, qW), qE), qS), qN);
-#endif
                     double dmx = mx - q, dmn = mn - q;
                     double phi = 0.0;
 #pragma unroll
@@ -362,11 +260,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         sQN[iFE(par, p, k, t)] = q + phi * term[p][2];
                         sQS[iQW(p, k)] = q + phi * term[p][3];
                     }
-#if PYH_COLD_HOOKS
                     if (want_grad_dbg) { if (full && outcol) hook_store1(B.dbgG, (8 + k) * (size_t)PL + o, phi); }
-#else
-                    if (want_grad_dbg && full && outcol) B.dbgG[(8 + k) * (size_t)PL + o] = phi;
-#endif
                 }
             } else {
 #pragma unroll
@@ -382,20 +276,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 }
             }
         }
-#if PYH_PAIR_BARRIER
-        // Only lanes next to a warp boundary exchange data with another warp (east-face states, west-face fluxes, the
-        // state ring at t +- 1), so each warp synchronises with its LEFT and its RIGHT neighbour only (named barriers
-        // of 64 threads) instead of the whole CTA: adjacent warps stay within one row of each other -- which is all
-        // the double-buffered rings need -- while the CTA as a whole may spread over several rows, so one warp waiting
-        // for memory no longer stalls the other three.
-        {
-            const int w = t >> 5, nw = NT >> 5;
-            if (w > 0) asm volatile("bar.sync %0, 64;" ::"r"(w) : "memory");
-            if (w < nw - 1) asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
-        }
-#else
         __syncthreads();
-#endif
 
         // ---- C(r): west face J = j of row r ----------------------------------------------------------
         double IW[4] = {0.0, 0.0, 0.0, 0.0};
@@ -466,7 +347,6 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 
         // ---- C(r): south face I = r of column j + D(r-1) ------------------------------------------------
         if (outcol && (r >= i0)) {
-#if PYH_D_EARLY
             double dA = 1.0, dS0[4] = {0.0, 0.0, 0.0, 0.0}, dS1[4] = {0.0, 0.0, 0.0, 0.0};
             auto load_d = [&]() {
                 const unsigned om_ = o - pitch;
@@ -477,10 +357,6 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                     dS1[k] = (plan.ntargets > 1) ? base[plan.t[1].src + k * PL + om_] : 0.0;
                 }
             };
-#endif
-#if PYH_D_EARLY == 2
-            if (r - 1 >= i0) load_d();
-#endif
             const double cf = PYH_RO(G[po.ch + o]), sf = PYH_RO(G[po.sh + o]), Lf = PYH_RO(G[po.Lh + o]);
             const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;
             const double Lfq = (flux_scale(FLUX) == 2.0) ? 0.5 * Lf : Lf;
@@ -545,14 +421,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             // D(r-1): residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89)
             if (r - 1 >= i0) {
                 const unsigned om = o - pitch;
-#if PYH_D_EARLY == 1
                 load_d();
-#endif
-#if PYH_D_EARLY
                 const double a = dA;
-#else
-                const double a = PYH_RO(G[po.A + om]);
-#endif
                 double Rk[4];
                 auto resid = [&](auto tag) -> bool {
                     constexpr bool FAST = decltype(tag)::value;
@@ -572,32 +442,44 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                 };
                 if (!resid(FastTag{})) resid(SafeTag{});
                 constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
-#if PYH_COLD_HOOKS
                 if (plan.write_residual) hook_store4(B.dbg, om, (size_t)PL, rscale * Rk[0], rscale * Rk[1], rscale * Rk[2], rscale * Rk[3]);
-#else
-                if (plan.write_residual) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) B.dbg[k * (size_t)PL + om] = PYH_FOLD_POW2 ? rscale * Rk[k] : Rk[k];
-                }
-#endif
                 {
                     // all source loads first, then the updates (targets 0 and 1 by static index: no local copies)
                     const int nt_ = plan.ntargets;
                     double s0[4], s1[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-#if PYH_D_EARLY
                         s0[k] = dS0[k];
                         s1[k] = dS1[k];
-#else
-                        s0[k] = (nt_ > 0) ? base[plan.t[0].src + k * PL + om] : 0.0;
-                        s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + om] : 0.0;
-#endif
                     }
                     if (nt_ > 0) {
                         const double c0 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[0].coef] : ctl->coef[plan.t[0].coef];
+                        double un[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) base[plan.t[0].dst + k * PL + om] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k];
+                        for (int k = 0; k < 4; ++k) { un[k] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k]; base[plan.t[0].dst + k * PL + om] = un[k]; }
+                        if (plan.fuse_dt) {
+                            // QuadBlock.get_dt (quad_block.py:423-436) + the realizability conditions (states/conservative.py:161-165) on
+                            // the state this step ends with, which is still in registers: the next step's Solver.get_dt costs no pass
+                            // over the state (k_dt does the same arithmetic as a kernel of its own for the first step of a run)
+                            const double cdx = PYH_RO(G[po.cdx + om]), cdy = PYH_RO(G[po.cdy + om]);
+                            double tx, ty;
+                            auto cfl = [&](auto tag) -> bool {
+                                constexpr bool FAST = decltype(tag)::value;
+                                bool ok = true;
+                                typename Ar<FAST>::R rr = Ar<FAST>::recip(un[0], ok);
+                                const double u = Ar<FAST>::div(un[1], rr, ok), v = Ar<FAST>::div(un[2], rr, ok);
+                                const double p = C.gm1 * (un[3] - un[0] * (0.5 * (u * u + v * v)));
+                                const double a_ = Ar<FAST>::sqrt(Ar<FAST>::div(C.g * p, rr, ok), ok);
+                                tx = Ar<FAST>::div(cdx, fabs(u) + a_, ok);
+                                ty = Ar<FAST>::div(cdy, fabs(v) + a_, ok);
+                                return ok;
+                            };
+                            if (!cfl(FastTag{})) cfl(SafeTag{});
+                            double tm = dmin2(tx, ty);
+                            // unrealizable (or NaN): -inf can never be a CFL time, so it doubles as the flag
+                            if (!(un[0] > 0.0) || !(un[3] > 0.0) || (tm != tm)) tm = __longlong_as_double(0xfff0000000000000ll);
+                            dtmin = dmin2(dtmin, tm);
+                        }
                     }
                     if (nt_ > 1) {
                         const double c1 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[1].coef] : ctl->coef[plan.t[1].coef];
@@ -620,6 +502,22 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 
         // rotate the ring
         const int tmp = sm; sm = sc; sc = sp; sp = tmp;
+    }
+    if (plan.fuse_dt) {   // block minimum -> one atomicMin per thread block (quad_block.py:436: min over cells; Solver.get_dt: over blocks)
+        // the rings are dead now: one of their rows serves as the reduction buffer
+        __syncthreads();
+        double* const sDT = smem;
+        sDT[t] = dtmin;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (t < s && t + s < NT) sDT[t] = dmin2(sDT[t], sDT[t + s]);
+            __syncthreads();
+        }
+        if (t == 0) {
+            const double m = sDT[0];
+            if (m == __longlong_as_double(0xfff0000000000000ll)) { atomicOr(&ctl_out->bad, 1); atomicExch(&ctl_out->allok, 0ull); }
+            else atomicMin(&ctl_out->dtmin_bits, dkey(m));
+        }
     }
 }
 

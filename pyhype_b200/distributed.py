@@ -120,21 +120,11 @@ class HaloExchanger:
         self.recvbuf = torch.zeros(max(ndoubles, 1), dtype=torch.float64, device=dev)
         self.empty = ndoubles == 0
         self.dt = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.comm = None
-        self.pending = None
-        self.overlap = False
-        # opt-in (PYH_HALO_OVERLAP=1): measured on 2 x B200 the blocking exchange costs ~35 us per stage while the
-        # dispatch-ordered launch it needs runs 0.2 ms slower there (profiles/r01k_halo_overlap.md), so it does not pay yet
-        if dev.type == "cuda" and not self.empty and os.environ.get("PYH_HALO_OVERLAP", "0") == "1":
-            capable, n_remote = engine.overlap_info()
-            # thread blocks that may wait for the exchange must never be able to fill the device alone
-            self.overlap = capable and n_remote <= 2 * torch.cuda.get_device_properties(dev).multi_processor_count
 
     def exchange(self):
         """pack -> grouped isend/irecv -> unpack (all on the current torch stream)."""
         if self.empty:
             return
-        self.wait()
         dist = self.dist
         self.engine.pack_halo(self.sendbuf.data_ptr())
         ops = []
@@ -145,43 +135,6 @@ class HaloExchanger:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         self.engine.unpack_halo(self.recvbuf.data_ptr())
-
-    # -- overlapped variant (CUDA only) ------------------------------------------------------------------
-    def exchange_async(self):
-        """pack on the compute stream, then send/recv + unpack on a communication stream; returns
-        (and remembers in ``self.pending``) the event after which the remote ghost frames are valid.
-        The next ``advance`` hands it to ``Engine.stage_overlapped`` so that only the thread blocks
-        next to remote edges wait for it."""
-        if self.empty:
-            return None
-        torch, dist = self.torch, self.dist
-        if self.comm is None:
-            self.comm = torch.cuda.Stream(device=self.sendbuf.device, priority=-1)
-            self._ev_packed = torch.cuda.Event()
-            self._ev_ready = torch.cuda.Event()
-        main = torch.cuda.current_stream(self.sendbuf.device)
-        self.engine.pack_halo(self.sendbuf.data_ptr())
-        self._ev_packed.record(main)
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(self._ev_packed)
-            ops = []
-            for peer, _k, off, ln in self.recvs:
-                ops.append(dist.P2POp(dist.irecv, self.recvbuf[off:off + ln], peer, group=self.group))
-            for peer, _k, off, ln in self.sends:
-                ops.append(dist.P2POp(dist.isend, self.sendbuf[off:off + ln], peer, group=self.group))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            self.engine.unpack_halo_on(self.recvbuf.data_ptr(), self.comm.cuda_stream)
-            self._ev_ready.record(self.comm)
-        self.pending = self._ev_ready
-        return self.pending
-
-    def wait(self):
-        """Make the compute stream wait for an outstanding asynchronous exchange (before anything
-        other than ``stage_overlapped`` reads remote ghost cells)."""
-        if self.pending is not None:
-            self.torch.cuda.current_stream(self.sendbuf.device).wait_event(self.pending)
-            self.pending = None
 
     def global_dt(self):
         """CFL * global min, left on the device (solvers/base.py:126-131)."""
@@ -198,18 +151,8 @@ def advance(engine, halo, num_stages, dt=None, dt_dev_ptr=None):
         engine.step_begin_dev(dt_dev_ptr)
     else:
         engine.step_begin(dt)
-    overlap = halo is not None and getattr(halo, "overlap", False)
     for s in range(num_stages):
-        if overlap:
-            # remote strips of this stage's input may still be in flight: only the thread blocks that
-            # read them wait; the exchange of the stage's output then runs behind the next stage
-            if halo.pending is not None:
-                engine.stage_overlapped(s)
-            else:
-                engine.stage(s)
-            halo.exchange_async()
-        else:
-            engine.stage(s)
-            if halo is not None:
-                halo.exchange()
+        engine.stage(s)
+        if halo is not None:
+            halo.exchange()
         engine.apply_bc()

@@ -208,16 +208,6 @@ class Engine:
     def stage(self, s):
         check(self.lib.pyh_stage(self._ctx, int(s)))
 
-    def stage_overlapped(self, s):
-        """Stage ``s`` as one launch whose thread blocks next to remote edges come last and wait for the
-        epoch stamp of the latest ``unpack_halo_on`` (see include/pyh_b200.h)."""
-        check(self.lib.pyh_stage_overlapped(self._ctx, int(s)))
-
-    def overlap_info(self):
-        cap, n = C.c_int32(0), C.c_int32(0)
-        check(self.lib.pyh_overlap_info(self._ctx, C.byref(cap), C.byref(n)))
-        return bool(cap.value), int(n.value)
-
     def run(self, t, t_final, max_steps=-1, poll_every=64, record_dts=0):
         """Device-resident time loop; returns (t, steps_done, unrealizable, dts)."""
         tt = C.c_double(float(t))
@@ -280,9 +270,6 @@ class Engine:
     def unpack_halo(self, dev_ptr):
         check(self.lib.pyh_unpack_halo(self._ctx, C.c_void_p(dev_ptr)))
 
-    def unpack_halo_on(self, dev_ptr, stream):
-        check(self.lib.pyh_unpack_halo_on(self._ctx, C.c_void_p(dev_ptr), C.c_uint64(int(stream))))
-
     # -- test hooks / counters ---------------------------------------------------------------------------
     def residual(self, gid):
         out = np.empty((self.ny, self.nx, 4))
@@ -293,6 +280,12 @@ class Engine:
         out = np.empty((self.ny, self.nx, 4))
         check(self.lib.pyh_debug_fetch(self._ctx, int(gid), {"gx": 0, "gy": 1, "phi": 2}[what], _dp(out)))
         return out
+
+    def march_shape(self):
+        """(lanes per thread block, rows per strip) of the stage kernel"""
+        a, b = C.c_int32(), C.c_int32()
+        check(self.lib.pyh_march_shape(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         n = C.c_int64()

@@ -118,3 +118,45 @@ def jet_ic(x, y):
     W = np.empty(x.shape + (4,))
     W[...] = np.array([1.0, 0.0, 0.0, 1 / GAMMA])
     return prim_to_cons_nd(W)
+
+
+# ---- synthetic weak-scaling explosion (BASELINE.json configs[4]) --------------------------
+WS_BLOCK_LEN = 1.25   # length units per block side
+
+
+def ws_mesh(n_rows, blocks_per_row):
+    """`blocks_per_row` x `n_rows` rectangular blocks (one row of 8 per GPU in the benchmark), reflection walls all round."""
+    return RectagularMeshGenerator.generate(
+        BCE=["Reflection"], BCW=["Reflection"], BCN=["Reflection"], BCS=["Reflection"],
+        east=WS_BLOCK_LEN * blocks_per_row, west=0.0, north=WS_BLOCK_LEN * n_rows, south=0.0,
+        n_blocks_horizontal=blocks_per_row, n_blocks_vertical=n_rows,
+    ).dict
+
+
+def ws_ic(x, y, width, height):
+    """Explosion box over the central 40 % of the domain (explosion_multi states), conservative, non-dimensional
+    (examples/explosion/initial_condition.py:35-60)."""
+    inside = (x >= 0.3 * width) & (x <= 0.7 * width) & (y >= 0.3 * height) & (y <= 0.7 * height)
+
+    def cons(rho, p):
+        e = p / (GAMMA - 1) + 0.0
+        return np.array([rho / 1.0, 0.0, 0.0, e / (1.0 * A_INF**2)])
+
+    hi, lo = cons(4.6968, 404400.0), cons(1.1742, 101100.0)
+    return np.where(inside[..., None], hi, lo)
+
+
+def ws_ic_smooth(x, y, width, height):
+    """Rounding-robust smooth field (IC-B): every face carries a genuine Riemann problem."""
+    rho = 1.2 + 0.3 * np.sin(0.7 * x + 0.3) * np.cos(0.45 * y + 0.1)
+    u = 30 * np.cos(0.5 * x) * np.sin(0.35 * y + 0.2)
+    v = -25 * np.sin(0.4 * x + 0.5) * np.cos(0.3 * y)
+    p = 101325 * (1 + 0.2 * np.cos(0.6 * x - 0.2) * np.sin(0.5 * y + 0.4))
+    ek = 0.5 * rho * (u * u + v * v)
+    U = np.stack((rho, rho * u, rho * v, p / (GAMMA - 1) + ek), axis=-1)
+    return U / np.array([1.0, A_INF, A_INF, A_INF**2])
+
+
+def ws_ic_1x1(x, y):
+    """the weak-scaling initial condition on a one-block domain (named fingerprint `ws2048`)"""
+    return ws_ic(x, y, WS_BLOCK_LEN, WS_BLOCK_LEN)

@@ -11,7 +11,21 @@ centroid offsets) is derived on the device by ``k_geometry``.
 """
 from __future__ import annotations
 
+import hashlib
+import os
+
 import numpy as np
+
+# Host geometry cache: arctan / arccos / cos / sin over (ny, nx) arrays cost ~1.5 s per
+# 2048 x 2048 block and stay on the host because libm's results are the contract (they are not reproducible bit for bit on
+# the device).  With PYH_GEOM_CACHE=<directory> every QuadMesh stores its arrays under a key of (nx, ny, the four vertices,
+# numpy's version) and later constructions with the same key load them instead (memory-mapped npy files, bit-identical by
+# construction since they ARE the earlier results).  Off by default: a cache directory is the user's decision.
+_CACHED = ("nodes_x", "nodes_y", "x", "y", "theta_v", "theta_h", "cos_v", "sin_v", "cos_h", "sin_h", "area")
+
+
+def _cache_dir():
+    return os.environ.get("PYH_GEOM_CACHE") or None
 
 
 class GridLocation:
@@ -30,7 +44,53 @@ class QuadMesh:
         self.nx, self.ny, self.nghost = int(nx), int(ny), nghost
         self.shape = (self.ny, self.nx)
         self.vertices = _Vertices(NE=NE, NW=NW, SE=SE, SW=SW)
-        self._create()
+        self.from_cache = False
+        if not self._load_cached():
+            self._create()
+            self._store_cached()
+        v = self.vertices
+        self.nodes = GridLocation(self.nodes_x[:, :, None], self.nodes_y[:, :, None])
+        self.A = self.area[:, :, None]
+        # BaseBlockGhost._is_cartesian (blocks/quad_block.py:96-113): exact corner comparison
+        self.is_cartesian = bool(
+            (v.NE[1] == v.NW[1]) and (v.SE[1] == v.SW[1]) and (v.SE[0] == v.NE[0]) and (v.SW[0] == v.NW[0])
+        )
+
+    def _cache_key(self):
+        v = self.vertices
+        corners = np.array([v.NE[0], v.NE[1], v.NW[0], v.NW[1], v.SE[0], v.SE[1], v.SW[0], v.SW[1]], dtype=np.float64)
+        h = hashlib.sha256(corners.tobytes() + f"|{self.nx}|{self.ny}|numpy {np.__version__}".encode())
+        return h.hexdigest()[:32]
+
+    def _load_cached(self):
+        d = _cache_dir()
+        if not d:
+            return False
+        path = os.path.join(d, self._cache_key())
+        if not os.path.exists(os.path.join(path, "complete")):
+            return False
+        try:
+            for name in _CACHED:
+                arr = np.load(os.path.join(path, name + ".npy"), mmap_mode="r")
+                setattr(self, name, arr[:, :, None] if name in ("x", "y") else arr)
+        except Exception:
+            return False
+        self.from_cache = True
+        return True
+
+    def _store_cached(self):
+        d = _cache_dir()
+        if not d:
+            return
+        path = os.path.join(d, self._cache_key())
+        try:
+            os.makedirs(path, exist_ok=True)
+            for name in _CACHED:
+                arr = getattr(self, name)
+                np.save(os.path.join(path, name + ".npy"), arr[:, :, 0] if name in ("x", "y") else arr)
+            open(os.path.join(path, "complete"), "w").close()
+        except OSError:
+            pass   # a read-only or full cache directory must not stop the run
 
     def _create(self):
         nx, ny, v = self.nx, self.ny, self.vertices
@@ -45,7 +105,6 @@ class QuadMesh:
             xn[r] = np.linspace(west_x[r], east_x[r], nx + 1)
             yn[r] = np.linspace(west_y[r], east_y[r], nx + 1)
         self.nodes_x, self.nodes_y = xn, yn
-        self.nodes = GridLocation(xn[:, :, None], yn[:, :, None])
         ne = (xn[1:, 1:], yn[1:, 1:])
         nw = (xn[1:, :-1], yn[1:, :-1])
         se = (xn[:-1, 1:], yn[:-1, 1:])
@@ -77,11 +136,6 @@ class QuadMesh:
         p1 = (s - s1) * (s - s2) * (s - s3) * (s - s4)
         p2 = s1 * s2 * s3 * s4
         self.area = np.sqrt(p1 - 0.5 * p2 * (1 + np.cos(a1 + a2)))
-        self.A = self.area[:, :, None]
-        # BaseBlockGhost._is_cartesian (blocks/quad_block.py:96-113): exact corner comparison
-        self.is_cartesian = bool(
-            (v.NE[1] == v.NW[1]) and (v.SE[1] == v.SW[1]) and (v.SE[0] == v.NE[0]) and (v.SW[0] == v.NW[0])
-        )
 
     # reference-style accessors (pyhype/mesh/quad_mesh.py:371-400)
     def get_NE_vertices(self):

@@ -9,7 +9,7 @@ from pyhype_b200.mesh.rectangular import RectagularMeshGenerator
 
 from pyhype_b200.examples import (  # noqa: F401  (shared with bench.py: the same inputs are benchmarked and tested)
     A_INF, GAMMA, RHO_INF, SIDES, _nd_inlet, dmr_ic, dmr_mesh, em_mesh, explosion_ic, jet_ic, jet_mesh, prim_to_cons_nd,
-    smooth_ic, wedge_ic, wedge_mesh,
+    smooth_ic, wedge_ic, wedge_mesh, ws_ic, ws_ic_1x1, ws_ic_smooth, ws_mesh,
 )
 
 

@@ -22,8 +22,6 @@ using pyh_host_twin::launch;
 
 static unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
-typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, const Consts, const int, const int,
-                        const int, const unsigned long long);
 // Only the instantiations the fixtures use are compiled (each costs ~1 s of g++): every flux x reconstruction mode with
 // the Venkatakrishnan limiter and one quadrature point; the other limiters and 2 / 3 points with Roe + conservative.
 static MarchFn pick(int f, int l, int p, int nq) {
@@ -74,7 +72,7 @@ struct Twin {
               const double* cos_h, const double* sin_h, const int* nbr, const int* bc, const int* is_cart, const double* dirichlet,
               const double* U) {
         nx = nx_; ny = ny_; nblk = nblk_; nq = nq_; nt = nt_; tys = tys_; prim = prim_;
-        if (nt < 32 || nt > 256 || nt % 32 || nq < 1 || nq > 3 || tys < 1 || S < 1 || S > PYH_MAX_STAGES) return -1;
+        if (nt < 6 || nt > 256 || nq < 1 || nq > 3 || tys < 1 || S < 1 || S > PYH_MAX_STAGES) return -1;
         fn = pick(flux, lim, prim, nq);
         if (!fn) return -2;   // instantiation not compiled into the twin
         lay.nx = nx; lay.ny = ny;
@@ -146,8 +144,16 @@ struct Twin {
     void ghost(int buf) {   // do_ghost
         launch(dim3(cdivu(mlen, 128), 4, nblk), 128, false, [&] { k_ghost(blks.data(), lay, po, po.H[buf], &ctl); });
     }
-    void stage(const StagePlan& plan, int want_grad_dbg) {   // launch_stage
-        launch(dim3(cdivu(nx, nt - 4), cdivu(ny, tys), nblk), nt, true, [&] { fn(blks.data(), lay, po, plan, &ctl, C, tys, want_grad_dbg, 0, 0ull); });
+    void stage(const StagePlan& plan, int want_grad_dbg) {   // launch_stage: the product's tile plan (PYH_TWIN_SPLIT = 1: north /
+        // south edge strips apart, 2: east / west edge columns apart, 3: both -- what a context with remote neighbours launches)
+        const char* e = getenv("PYH_TWIN_SPLIT");
+        const int split = e ? atoi(e) : 0;
+        TileLaunch tl[3];
+        const int n = plan_tiles(nx, ny, nt, tys, (split & 1) != 0, (split & 2) != 0, tl);
+        for (int q = n - 1; q >= 0; --q) {   // interior first, edges last: the order must not matter
+            const TileLaunch t = tl[q];
+            launch(dim3(t.gx, t.gy, nblk), nt, true, [&] { fn(blks.data(), lay, po, plan, &ctl, &ctl, C, t.tys, want_grad_dbg, t.tiles); });
+        }
     }
     void fetch_state(int buf, double* out) const {
         for (int b = 0; b < nblk; ++b)
@@ -259,13 +265,16 @@ int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int 
         launch(dim3(cdivu(nx, 256), cdivu(ny, DT_ROWS), nblk), 256, true,
                [&] { k_dt(T.blks.data(), T.lay, T.po, T.po.H[buf], nblk, &ctl, T.C, respect_active); });
     };
+    // pyh_run: the CFL minimum of the starting state by k_dt, afterwards by the last stage of every step (plan.fuse_dt)
+    dt_kernel(i0, 0);
     for (int n = 0; n < max_steps; ++n) {                 // enqueue_step
-        dt_kernel(i0, 1);
         k_dt_finalize(&ctl, cfl, tb, 0, nullptr);
         for (int s = 0; s < S; ++s) {
             cur = (s == 0) ? i0 : cur;
             const int next = plan_next_buffer(S, s, cur, i0, i1, i2);
-            T.stage(plan_stage(tab, S, T.po, i0, s, cur, next), 0);
+            StagePlan pl = plan_stage(tab, S, T.po, i0, s, cur, next);
+            pl.fuse_dt = (s == S - 1) ? 1 : 0;
+            T.stage(pl, 0);
             cur = next;
             if (s == S - 1) {
                 if (S == 1) std::swap(i0, i1);
@@ -276,8 +285,7 @@ int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int 
         k_step_end(&ctl);
         if (!ctl.active || ctl.bad || !(ctl.t < ctl.t_final)) break;
     }
-    dt_kernel(i0, 0);                                     // final realizability check of the last state
-    double tmp = 0.0;
+    double tmp = 0.0;                                     // final realizability check: the flag the last step reduced
     k_dt_finalize(&ctl, cfl, tb, 1, &tmp);
     T.fetch_state(i0, Uout);
     *t_out = ctl.t;

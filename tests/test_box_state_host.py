@@ -76,3 +76,27 @@ def test_box_on_top_of_host_data_is_applied_on_the_host():
     assert [c[0] for c in sync.calls] == ["upload"]
     x = mesh.x[:, :, 0]
     assert np.array_equal(sync.calls[0][1], np.where((x <= 5.0)[..., None], mark, base))
+
+
+def test_stale_alias_contract_is_what_the_docstring_says():
+    """an array kept across a device call is a stale copy; re-reading .data downloads, the setter always wins."""
+    st, sync, mesh = _state()
+
+    class Dev(RecordingSync):
+        def download(self):
+            self.calls.append(("download",))
+            return np.full((10, 12, 4), 7.0)
+
+    dev = Dev(mesh)
+    st._sync = dev
+    st.data = np.ones((10, 12, 4))
+    alias = st.data
+    st.push_if_touched()
+    st.mark_device_newer()                 # a solver call happened
+    alias[...] = 0.0                       # stale write: not tracked
+    st.push_if_touched()
+    assert [c[0] for c in dev.calls] == ["upload"]
+    assert np.all(st.data == 7.0)          # fresh download
+    st.data = np.full((10, 12, 4), 3.0)    # the setter always takes effect
+    st.push_if_touched()
+    assert dev.calls[-1][0] == "upload" and np.all(dev.calls[-1][1] == 3.0)

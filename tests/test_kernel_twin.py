@@ -30,10 +30,12 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
 
-# extra -D flags of the builds that are checked: the shipped default and the opt-in variants waiting for GPU time
-BUILDS = {"default": [], "tight": ["-DPYH_LEAN_CHECKS=1", "-DPYH_COLD_HOOKS=1", "-DPYH_D_EARLY=1"],
-          "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0"], "uniform_shortcut": ["-DPYH_UNIFORM_SHORTCUT=1"],
-          "early_loads_unrolled_cert": ["-DPYH_D_EARLY=2", "-DPYH_B_GEOM_FIRST=1", "-DPYH_UNROLL_B1=2", "-DPYH_UNROLL_B2=2", "-DPYH_HARTEN_CERT=1", "-DPYH_MINMAX_NET=1"]}
+# extra -D flags of the builds that are checked: the shipped default (folded power-of-two scalings, lean range checks, certified
+# Harten test), the literal operation list of SURVEY.md section 8A with every check, and the opt-in uniform-flow shortcut
+BUILDS = {"default": [],
+          "literal": ["-DPYH_FOLD_POW2=0", "-DPYH_SKIP_UNIT_ROT=0", "-DPYH_LEAN_CHECKS=0", "-DPYH_HARTEN_CERT=0"],
+          "full_checks": ["-DPYH_LEAN_CHECKS=0", "-DPYH_HARTEN_CERT=0"],
+          "uniform_shortcut": ["-DPYH_UNIFORM_SHORTCUT=1"]}
 
 
 def build(name):
@@ -293,3 +295,17 @@ def test_device_resident_time_loop_source_flags_unrealizable_states(lib_default)
     fx.z[f"U0_{g0}"] = U
     idx, Uout, dts, t, nsteps, bad = run_loop(lib_default, fx, 0.0, 1e9, 3)
     assert bad and nsteps == 0
+
+
+@pytest.mark.parametrize("split", [1, 2, 3])
+@pytest.mark.parametrize("name,nt,tys", [("em_roe_venkat_cons_rk4", 12, 4), ("jet_hlll_prim_rk2", 16, 4), ("wedge_hlll_prim_rk2", 10, 3)])
+def test_edge_and_interior_launches_cover_every_cell_once(lib_default, monkeypatch, name, nt, tys, split):
+    """A context with remote neighbours launches every stage as thin edge strips (first / last rows, first / last column strip)
+    plus an interior launch (pyh_plan.cuh: plan_tiles) so that the strip exchange runs behind the interior.  The twin runs the
+    same tile plan -- interior FIRST, edges last, i.e. not even in the product's order -- and must reproduce the reference's
+    ghost strips, gradients, limiter, residual and updated state exactly as the single launch does."""
+    monkeypatch.setenv("PYH_TWIN_SPLIT", str(split))
+    fx = golden_io.Fixture(name)
+    coef = 0.37 * float(fx["dts"][0])
+    out = run_stage(lib_default, fx, nt=nt, tys=tys, coef=coef)
+    check(fx, *out, coef)

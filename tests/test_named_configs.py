@@ -1,6 +1,9 @@
 """BASELINE.json's named configurations at their NAMED sizes against fingerprints of the unmodified reference
 (tests/golden/named/*.npz, written by oracle/make_named_fingerprints.py in the build container):
 
+* the weak-scaling block of bench.py: one block of 1024 x 1024 against the unmodified reference (the largest its object model
+  fits in the build container), first 2 RK4 steps; and the headline size itself, one block of 2048 x 2048, first step, against the
+  numpy restatement (`ws2048`, labelled so in its metadata);
 * examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall, 15 degree ramp), with
   the shipped HLLL flux and with the Roe flux BASELINE.json names, first 50 steps;
 * examples/jet at its shipped size (9 stacked blocks of 1080 x 60, slip walls + Dirichlet inlet), shipped HLLL flux, first 50
@@ -75,7 +78,7 @@ class Named:
             assert value_digest(U) == self.meta["digests"][f"{n}_{g}"], (self.name, n, g, np.abs(sub - ref).max())
 
 
-ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle"]
+ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle", "ws1024", "ws2048"]
 
 
 @pytest.mark.gpu
@@ -106,7 +109,7 @@ def test_named_config_at_named_size_reproduces_the_reference(name):
         eng.close()
 
 
-@pytest.mark.parametrize("name", ALL_NAMED)
+@pytest.mark.parametrize("name", [n for n in ALL_NAMED if n != "ws2048"])   # ws2048 IS the oracle's output (3 minutes of numpy)
 def test_oracle_restatement_at_named_size_first_checkpoint(name):
     fp = Named(name)
     n = fp.meta["checkpoints"][0]

@@ -163,7 +163,8 @@ void choose_march_shape(Ctx* c) {
     const long long nblk = (long long)std::max<size_t>(c->blocks.size(), 1);
     const int nq = c->cfg.num_quadrature_points;
     MarchFn fn = pick_march(c->cfg.flux, c->cfg.limiter, c->cfg.recon, nq);
-    cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * MARCH_MAX_THREADS * (int)sizeof(double));
+    const int maxt = march_max_threads(nq);
+    cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * maxt * (int)sizeof(double));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
     auto slots_for = [&](int n) -> long long {
@@ -177,7 +178,7 @@ void choose_march_shape(Ctx* c) {
     double best = -1.0;
     int nt = 128;
     for (int n : cand) {
-        if (n > MARCH_MAX_THREADS) continue;
+        if (n > 128) continue;   // large problems: 4 thread blocks of 128 threads per SM is the measured optimum
         int strips = (nx + n - 5) / (n - 4);
         double util = (double)nx / ((double)strips * n);
         if (util > best + 1e-9 || (util > best - 1e-9 && n > nt)) { best = util; nt = n; }
@@ -195,7 +196,7 @@ void choose_march_shape(Ctx* c) {
     if (n_ctas(nt, tys) <= 3 * slots_for(nt)) {   // small problem: cheapest (nt, tys) by the wave model
         double best_cost = 1e300;
         for (int n : cand) {
-            if (n > MARCH_MAX_THREADS) continue;
+            if (n > maxt) continue;
             const long long slots = slots_for(n);
             for (int ty = 2; ty <= std::min(ny, 128); ++ty) {
                 const long long ctas = n_ctas(n, ty);
@@ -206,7 +207,7 @@ void choose_march_shape(Ctx* c) {
             }
         }
     }
-    if (const char* e = getenv("PYH_MARCH_NT")) { int v = atoi(e); if (v >= 32 && v <= MARCH_MAX_THREADS && v % 32 == 0) nt = v; }
+    if (const char* e = getenv("PYH_MARCH_NT")) { int v = atoi(e); if (v >= 32 && v <= maxt && v % 32 == 0) nt = v; }
     if (const char* e = getenv("PYH_MARCH_TYS")) { int v = atoi(e); if (v >= 1) tys = v; }
     c->march_nt = nt;
     c->march_tys = tys;
@@ -219,7 +220,7 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg, const TileLau
     const int nt = c->march_nt;
     size_t smem = (size_t)march_smem_doubles(nq) * nt * sizeof(double);
     if (!c->march_configured) {   // per context = per device (the attribute is a per-device property of the function)
-        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * MARCH_MAX_THREADS * (int)sizeof(double)));
+        CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, march_smem_doubles(nq) * march_max_threads(nq) * (int)sizeof(double)));
         if (const char* e = getenv("PYH_CARVEOUT")) CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         c->march_configured = true;
     }

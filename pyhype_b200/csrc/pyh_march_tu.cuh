@@ -4,13 +4,17 @@
 #include "pyh_math.cuh"
 
 namespace pyh {
+// Launch bounds.  One quadrature point: up to 160 threads (156 output columns: one strip covers explosion_multi's 150-column
+// blocks) at >= 3 thread blocks per SM.  The SAME code also runs as 4 thread blocks of 128 threads -- the shape of large
+// problems -- as long as ptxas stays within 128 registers, which it does (126-128) and which tests/test_abi.py enforces
+// (-maxrregcount is ignored for kernels with launch bounds).  2 / 3 points need more shared memory per thread: 128 threads.
 #ifndef PYH_MARCH_MAXT
-#define PYH_MARCH_MAXT 128
+#define PYH_MARCH_MAXT 160
 #endif
 #ifndef PYH_MARCH_MINB
-#define PYH_MARCH_MINB 4
+#define PYH_MARCH_MINB 3
 #endif
-constexpr int MARCH_MAX_THREADS = PYH_MARCH_MAXT;
+constexpr int march_max_threads(int nq) { return nq == 1 ? PYH_MARCH_MAXT : 128; }
 
 // Which strips of every block one launch of the stage kernel covers.  A plain launch covers the whole block; a context with remote
 // neighbours splits every stage into an EDGE launch (the thin strips that produce the cells other ranks need) and an INTERIOR

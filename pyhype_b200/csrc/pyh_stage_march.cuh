@@ -63,7 +63,7 @@ typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
 template <int FLUX, int LIM, int PRIM, int NQ>
-__global__ void __launch_bounds__(MARCH_MAX_THREADS, march_min_blocks(NQ))
+__global__ void __launch_bounds__(march_max_threads(NQ), march_min_blocks(NQ))
 k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
               const Control* __restrict__ ctl, Control* __restrict__ ctl_out, const Consts C, const int tys, const int want_grad_dbg,
               const MarchTiles tiles) {

@@ -51,3 +51,29 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_stage_kernel_register_budget():
+    """The one-quadrature-point stage kernels are built with launch bounds (160 threads, 3 blocks) so that explosion_multi's
+    150-column blocks fit one strip, but the large-problem shape is 4 thread blocks of 128 threads per SM: that needs <= 128
+    registers per thread, which nvcc's -maxrregcount cannot enforce on a kernel with launch bounds.  ptxas stays within 128
+    today; this test fails the build the day an edit pushes it over (occupancy would silently drop to 3 blocks)."""
+    import shutil
+    import subprocess
+
+    from pyhype_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the library not available")
+    out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    lines = out.splitlines()
+    seen = 0
+    for i, ln in enumerate(lines):
+        m = re.search(r"Function _ZN3pyh13k_stage_marchILi(\d)ELi(\d)ELi(\d)ELi(\d)EE", ln)
+        if not m or m.group(4) != "1":
+            continue
+        regs = int(re.search(r"REG:(\d+)", lines[i + 1]).group(1))
+        seen += 1
+        assert regs <= 128, f"k_stage_march<{m.group(1)},{m.group(2)},{m.group(3)},1> uses {regs} registers: 4 x 128 threads no longer fit an SM"
+    assert seen == 24, seen

@@ -39,8 +39,9 @@ from pyhype_b200.examples import WS_BLOCK_LEN as BLOCK_LEN, ws_ic, ws_ic_smooth,
 
 BYTES_PER_CELL_STEP = {"RK4": 512.0, "RK2": 160.0, "ExplicitEuler1": 64.0}
 # FP64 instructions (DFMA + DMUL + DADD + DSETP) per cell-stage of the headline scheme, counted by ncu on the shipped build
-# (profiles/: r01s 1152 with the exact power-of-two scalings folded; the literal operation list of SURVEY.md section 8A needs 1187)
-FP64_INSTR_PER_CELL_STAGE = 1152
+# (profiles/r02d_stage_march_ncu_summary.txt: 44.5 % of 2475 warp instructions per cell; r01s had 1152 before the Harten certificate
+# and the min/max network; the literal operation list of SURVEY.md section 8A needs 1187)
+FP64_INSTR_PER_CELL_STAGE = 1101
 
 
 def load_peaks():
@@ -395,11 +396,10 @@ def run_ours(args):
     ok = eng.realizable()
 
     # ---- the dominant kernel alone: events on the launching stream around every stage launch of two more steps
-    dt_dev = torch.zeros(1, dtype=torch.float64, device=f"cuda:{lrank}")
     stage_ev = []
     for _ in range(2):
-        eng.local_dt(dt_dev.data_ptr())
-        eng.step_begin_dev(dt_dev.data_ptr())
+        eng.local_dt()          # dt stays in the context's device scratch
+        eng.step_begin_dev()
         for s in range(nstages):
             a = timer.event(); eng.stage(s); b_ = timer.event()
             eng.apply_bc()
@@ -452,10 +452,14 @@ def run_ours(args):
     # max over ranks
     cells_local = len(mine) * n * n
     sus_ms = sustained[0] if sustained else 0.0
+    kern_per_rank = None
     if dist is not None:
         tt = torch.tensor([ms, e2e_s, sus_ms], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_s, sus_ms = float(tt[0]), float(tt[1]), float(tt[2])
+        kk = [torch.zeros(1, dtype=torch.float64) for _ in range(wsize)]
+        dist.all_gather(kk, torch.tensor([float(np.mean(stage_ms))], dtype=torch.float64))
+        kern_per_rank = [float(x[0]) for x in kk]   # chip-to-chip spread: every step waits for the slowest rank
         cc = torch.tensor([cells_local, launches], dtype=torch.float64)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         cells_total, launches_total = int(cc[0]), int(cc[1])
@@ -468,7 +472,7 @@ def run_ours(args):
     value = cells_total * nstages * args.steps / (ms * 1e-3)
     e2e_value = cells_total * nstages * e2e_steps / e2e_s
     bytes_per_cell_stage = BYTES_PER_CELL_STEP.get(integ, 128.0 * nstages) / nstages
-    kern_ms = float(np.mean(stage_ms))
+    kern_ms = float(np.mean(stage_ms)) if kern_per_rank is None else max(kern_per_rank)
     achieved = cells_local * bytes_per_cell_stage / (kern_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
@@ -507,7 +511,7 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src,
-            "peak_source": peak_src, "kernel": "k_stage_march", "kernel_ms_avg": kern_ms,
+            "peak_source": peak_src, "kernel": "k_stage_march", "kernel_ms_avg": kern_ms, "kernel_ms_avg_per_rank": kern_per_rank,
             "algorithmic_bytes_per_cell_stage": bytes_per_cell_stage, "cells_per_launch": cells_local,
             "binding_resource": "fp64_pipe",
             "fp64_pipe": {

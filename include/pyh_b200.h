@@ -155,7 +155,8 @@ int pyh_pack_halo(void* ctx, double* dev_send);
 int pyh_unpack_halo(void* ctx, const double* dev_recv);
 
 /* Solver.get_dt (pyhype/solvers/base.py:114-136) + QuadBlock.get_dt (quad_block.py:423-436).
- * pyh_local_dt writes CFL * min over this context's blocks to a device double (no clamp);
+ * pyh_local_dt writes CFL * min over this context's blocks (over all ranks after pyh_comm_init) to a device double (no
+ * clamp; NULL = a scratch double owned by the context, which pyh_step_begin_dev(ctx, NULL) reads back);
  * pyh_get_dt additionally applies the (t_final - t) clamp and returns it on the host. */
 int pyh_local_dt(void* ctx, double* dev_dt_out);
 int pyh_get_dt(void* ctx, double t, double t_final, double* dt_out);

@@ -319,13 +319,23 @@ int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
     static const bool no_overlap = getenv("PYH_NO_HALO_OVERLAP") != nullptr;   // diagnostics: blocking exchange behind one launch
     StagePlan p = advance_roles(c, s, fuse_dt);
     int rc;
-    if (!c->comm.comm || c->slots.empty() || no_overlap || !c->s_edge) {
+    static const bool force_split = getenv("PYH_FORCE_SPLIT") != nullptr;      // diagnostics: the edge / interior split on ONE rank
+    if (force_split && !c->s_edge && !c->blocks.empty()) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->s_edge, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_edge_done, cudaEventDisableTiming));
+        c->split_ns = true;
+    }
+    if (!force_split && (!c->comm.comm || c->slots.empty() || no_overlap || !c->s_edge)) {
         if ((rc = launch_stage(c, p, 0))) return rc;
         if ((rc = exchange_halo(c, c->cur))) return rc;
         return do_ghost(c, c->cur);
     }
     TileLaunch tl[3];
-    const int n = plan_tiles(c->lay.nx, c->lay.ny, c->march_nt, c->march_tys, c->split_ns, c->split_ew, tl);
+    static const int edge_rows = getenv("PYH_EDGE_ROWS") ? std::max(1, atoi(getenv("PYH_EDGE_ROWS"))) : kEdgeRows;   // diagnostics
+    const int n = plan_tiles(c->lay.nx, c->lay.ny, c->march_nt, c->march_tys, c->split_ns, c->split_ew, tl, edge_rows);
     CU(cudaEventRecord(c->ev_fork, c->stream));
     CU(cudaStreamWaitEvent(c->s_edge, c->ev_fork, 0));
     for (int q = 0; q < n; ++q)
@@ -806,7 +816,7 @@ int pyh_local_dt(void* ctx, double* dev_dt_out) {
     int rc = launch_dt(c, c->i0);
     if (rc) return rc;
     if ((rc = reduce_dt(c))) return rc;   // with pyh_comm_init: the GLOBAL minimum
-    k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, dev_dt_out);
+    k_dt_finalize<<<1, 1, 0, c->stream>>>(c->d_ctl, c->cfg.cfl, c->tab, 1, dev_dt_out ? dev_dt_out : c->d_tmp);   // NULL: the context's own scratch
     CU(cudaGetLastError());
     c->launches++;
     return 0;
@@ -838,7 +848,7 @@ int pyh_step_begin(void* ctx, double dt) {
 int pyh_step_begin_dev(void* ctx, const double* dev_dt) {
     Ctx* c = as_ctx(ctx);
     if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
-    if (!dev_dt) return set_err(PYH_ERR_INVALID, "null pointer");
+    if (!dev_dt) dev_dt = c->d_tmp;   // NULL: the value the last pyh_local_dt(ctx, NULL) left in the context's scratch
     CU(cudaSetDevice(c->cfg.device));
     k_set_dt<<<1, 1, 0, c->stream>>>(c->d_ctl, 0.0, dev_dt, c->tab);
     CU(cudaGetLastError());

@@ -81,10 +81,9 @@ struct TileLaunch {
 // write disjoint cells and all read the same input buffer, so they may run concurrently and in any order; together they
 // cover every cell exactly once (tests/test_kernel_twin.py runs the split on the CPU).  Returns the number of launches.
 constexpr int kEdgeRows = 4;
-inline int plan_tiles(int nx, int ny, int nt, int tys, bool split_ns, bool split_ew, TileLaunch out[3]) {
+inline int plan_tiles(int nx, int ny, int nt, int tys, bool split_ns, bool split_ew, TileLaunch out[3], int th = kEdgeRows) {
     const int nsx = (nx + nt - 5) / (nt - 4);
     int n = 0;
-    const int th = kEdgeRows;
     if (split_ns && ny < 2 * th + 1) split_ns = false;   // tiny blocks: nothing left to overlap with
     const int mid0 = split_ns ? th : 0, mid1 = split_ns ? ny - th : ny;
     if (split_ew && nsx < 3) split_ew = false;           // the two edge column strips would be the whole block

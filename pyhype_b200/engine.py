@@ -193,8 +193,9 @@ class Engine:
         check(self.lib.pyh_get_dt(self._ctx, float(t), float(t_final), C.byref(dt)))
         return dt.value
 
-    def local_dt(self, dev_ptr):
-        check(self.lib.pyh_local_dt(self._ctx, C.c_void_p(dev_ptr)))
+    def local_dt(self, dev_ptr=None):
+        """CFL * min on the device (global after comm_init); None keeps it in the context's own scratch double."""
+        check(self.lib.pyh_local_dt(self._ctx, C.c_void_p(dev_ptr) if dev_ptr else None))
 
     def step(self, dt):
         check(self.lib.pyh_step(self._ctx, float(dt)))
@@ -202,8 +203,8 @@ class Engine:
     def step_begin(self, dt):
         check(self.lib.pyh_step_begin(self._ctx, float(dt)))
 
-    def step_begin_dev(self, dev_ptr):
-        check(self.lib.pyh_step_begin_dev(self._ctx, C.c_void_p(dev_ptr)))
+    def step_begin_dev(self, dev_ptr=None):
+        check(self.lib.pyh_step_begin_dev(self._ctx, C.c_void_p(dev_ptr) if dev_ptr else None))
 
     def stage(self, s):
         check(self.lib.pyh_stage(self._ctx, int(s)))

@@ -30,7 +30,13 @@ def main():
     nbx, nby = (int(v) for v in os.environ.get("PYH_TEST_LAYOUT", "2x4").split("x"))
     mesh = em_mesh() if (nbx, nby) == (2, 4) else cases.em_mesh(nbx=nbx, nby=nby)
     sim = Euler2D(config=config, mesh_config=mesh)
-    sim.solve()
+    if os.environ.get("PYH_TEST_MODE") == "step":
+        # the reference's loop body one call at a time (Euler2D.py:199-210): collective get_dt / integrate / realizability check
+        sim._pre_process_solve()
+        while sim.t < sim.t_final:
+            sim.step()
+    else:
+        sim.solve()
     prob = cases.build_oracle(mesh.dict if hasattr(mesh, "dict") else mesh, nx, ny, cases.explosion_ic, integrator=integ, CFL=cfl)
     t, dts = prob.run(0.0, 0.004 * 343.0)
     assert sim.num_time_step == len(dts) and sim.t == t, (sim.num_time_step, len(dts))

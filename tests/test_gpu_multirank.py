@@ -50,6 +50,20 @@ def test_single_stage_tableau_sharded():
     _run(2, 29562, PYH_TEST_INTEGRATOR="ExplicitEuler1")
 
 
+def test_step_by_step_driving_is_collective_and_bit_identical():
+    """Euler2D.step() (get_dt -> integrate -> realizability check per call, two host syncs per step) instead of the device loop"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, 29566, PYH_TEST_MODE="step")
+
+
+def test_blocking_exchange_switch():
+    """PYH_NO_HALO_OVERLAP=1: one launch per stage, exchange behind it (the diagnostic order) gives the same bits"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, 29568, PYH_NO_HALO_OVERLAP="1")
+
+
 def test_more_ranks_than_blocks():
     """2 blocks on 4 ranks: ranks 2 and 3 own nothing and only take part in the reductions (the reference tolerates idle
     ranks: `if len(self._blocks)` in Euler2D._solve, np.inf in get_dt)."""

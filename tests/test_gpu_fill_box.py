@@ -91,3 +91,26 @@ def test_box_initial_condition_state_is_readable_before_solve():
     for blk in sim.blocks:
         ref = cases.explosion_ic(blk.mesh.x[:, :, 0], blk.mesh.y[:, :, 0])
         assert np.array_equal(blk.state.data, ref)
+
+
+def test_weak_scaling_box_equals_the_numpy_initial_condition():
+    """bench.py fills its explosion box on the device (no 1 GiB upload per GPU): the same states and bounds must give what
+    pyhype_b200.examples.ws_ic evaluates on the host, block by block, on a 3 x 2 grid of rectangular blocks."""
+    blocks = cases.ws_mesh(2, 3)
+    width, height = 3 * 1.25, 2 * 1.25
+    eng = _engine(blocks, 40, 36)
+    try:
+        hi = cases.ws_ic(np.array([[0.5 * width]]), np.array([[0.5 * height]]), width, height)[0, 0]
+        lo = cases.ws_ic(np.array([[0.0]]), np.array([[0.0]]), width, height)[0, 0]
+        for g in blocks:
+            eng.fill_box(g, 0.3 * width, 0.7 * width, 0.3 * height, 0.7 * height, hi, lo)
+        n_in = 0
+        for g in blocks:
+            m = eng.meshes[g]
+            ref = cases.ws_ic(m.x[:, :, 0], m.y[:, :, 0], width, height)
+            got = eng.download(g)
+            assert np.array_equal(got, ref), g
+            n_in += int((got[..., 0] == hi[0]).sum())
+        assert 0 < n_in < 6 * 40 * 36
+    finally:
+        eng.close()

@@ -84,9 +84,13 @@ constexpr int kEdgeRows = 4;
 inline int plan_tiles(int nx, int ny, int nt, int tys, bool split_ns, bool split_ew, TileLaunch out[3], int th = kEdgeRows) {
     const int nsx = (nx + nt - 5) / (nt - 4);
     int n = 0;
-    if (split_ns && ny < 2 * th + 1) split_ns = false;   // tiny blocks: nothing left to overlap with
+    // A requested split that the block is too small for (fewer than 2 th + 1 rows / fewer than 3 column strips) must not
+    // leave cells a neighbour rank needs in the interior launch: the exchange would pack them before they are written.
+    // Then nothing is split and the one launch counts as "edge" (the exchange follows it: the blocking order).
+    const bool can_ns = ny >= 2 * th + 1, can_ew = nsx >= 3;
+    if ((split_ns && !can_ns) || (split_ew && !can_ew)) split_ns = split_ew = false;
+    const bool any_split = split_ns || split_ew;
     const int mid0 = split_ns ? th : 0, mid1 = split_ns ? ny - th : ny;
-    if (split_ew && nsx < 3) split_ew = false;           // the two edge column strips would be the whole block
     if (split_ns) {       // rows [0, th) and [ny - th, ny), every column strip
         TileLaunch t;
         t.tiles = MarchTiles{0, ny - th, ny, 0, 1};
@@ -100,9 +104,9 @@ inline int plan_tiles(int nx, int ny, int nt, int tys, bool split_ns, bool split
         t.gx = 2; t.gy = (unsigned)gy_mid; t.edge = 1; t.tys = tys;
         out[n++] = t;
     }
-    TileLaunch t;         // the rest
+    TileLaunch t;         // the rest: the interior -- or, without any split, the whole block (then the exchange waits for it)
     t.tiles = MarchTiles{mid0, tys, mid1, split_ew ? 1 : 0, 1};
-    t.gx = (unsigned)(split_ew ? nsx - 2 : nsx); t.gy = (unsigned)gy_mid; t.edge = (split_ns || split_ew) ? 0 : 1; t.tys = tys;
+    t.gx = (unsigned)(split_ew ? nsx - 2 : nsx); t.gy = (unsigned)gy_mid; t.edge = any_split ? 0 : 1; t.tys = tys;
     out[n++] = t;
     return n;
 }

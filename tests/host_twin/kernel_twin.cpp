@@ -294,4 +294,17 @@ int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int 
     return 0;
 }
 
+// pyh_plan.cuh: plan_tiles as data, for tests/test_kernel_twin.py (coverage and edge-before-exchange invariants).
+// out: per launch {row0, rowstride, row1, xfirst, xstride, gx, gy, tys, edge}; returns the number of launches.
+int twin_plan_tiles(int nx, int ny, int nt, int tys, int split_ns, int split_ew, int* out) {
+    TileLaunch tl[3];
+    const int n = plan_tiles(nx, ny, nt, tys, split_ns != 0, split_ew != 0, tl);
+    for (int q = 0; q < n; ++q) {
+        const int v[9] = {tl[q].tiles.row0, tl[q].tiles.rowstride, tl[q].tiles.row1, tl[q].tiles.xfirst, tl[q].tiles.xstride,
+                          (int)tl[q].gx, (int)tl[q].gy, tl[q].tys, tl[q].edge};
+        for (int i = 0; i < 9; ++i) out[9 * q + i] = v[i];
+    }
+    return n;
+}
+
 }  // extern "C"

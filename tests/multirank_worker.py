@@ -21,14 +21,15 @@ def main():
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    nx, ny = 26, 22
+    nx, ny = int(os.environ.get("PYH_TEST_NX", "26")), int(os.environ.get("PYH_TEST_NY", "22"))
     integ = os.environ.get("PYH_TEST_INTEGRATOR", "RK4")
     cfl = 0.3 if integ == "ExplicitEuler1" else 0.7
     config = em_config(nx=nx, ny=ny, t_final=0.004, initial_condition=ExplosionInitialCondition(), time_integrator=integ, CFL=cfl)
     # PYH_TEST_LAYOUT = "NBXxNBY": default 2x4 (rank boundaries between block rows); "2x1" with 2 ranks puts the rank
     # boundary on an east / west edge
     nbx, nby = (int(v) for v in os.environ.get("PYH_TEST_LAYOUT", "2x4").split("x"))
-    mesh = em_mesh() if (nbx, nby) == (2, 4) else cases.em_mesh(nbx=nbx, nby=nby)
+    north = float(os.environ.get("PYH_TEST_NORTH", "20.0"))   # 10.0 with a 2x2 layout puts the explosion box across BOTH interfaces
+    mesh = em_mesh() if (nbx, nby) == (2, 4) else cases.em_mesh(nbx=nbx, nby=nby, north=north)
     sim = Euler2D(config=config, mesh_config=mesh)
     if os.environ.get("PYH_TEST_MODE") == "step":
         # the reference's loop body one call at a time (Euler2D.py:199-210): collective get_dt / integrate / realizability check

@@ -43,6 +43,23 @@ def test_rank_boundary_on_east_west_edge():
     _run(2, 29560, PYH_TEST_LAYOUT="2x1")
 
 
+def test_rank_boundaries_on_all_four_sides_small_blocks():
+    """2 x 2 blocks on 4 ranks: every rank meets other ranks across an east / west AND a north / south edge.  26 x 22 blocks are
+    too narrow to split off edge column strips, so the tile plan must fall back to one launch + exchange (the 8-rank run of the
+    2 x 4 layout caught a plan that packed the east / west columns before the interior launch had written them)."""
+    if _ngpu() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run(4, 29570, PYH_TEST_LAYOUT="2x2", PYH_TEST_NORTH="10.0")
+
+
+def test_rank_boundaries_on_all_four_sides_both_splits_active():
+    """same layout with 90 x 40 blocks and 32-lane strips: 4 column strips, so the north / south edge rows AND the east / west
+    edge column strips run ahead of the exchange and the interior overlaps it"""
+    if _ngpu() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run(4, 29572, PYH_TEST_LAYOUT="2x2", PYH_TEST_NORTH="10.0", PYH_TEST_NX="90", PYH_TEST_NY="40", PYH_MARCH_NT="32")
+
+
 def test_single_stage_tableau_sharded():
     """ExplicitEuler1 alternates two state buffers: the exchange must follow the buffer the stage wrote."""
     if _ngpu() < 2:

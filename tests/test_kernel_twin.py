@@ -309,3 +309,44 @@ def test_edge_and_interior_launches_cover_every_cell_once(lib_default, monkeypat
     coef = 0.37 * float(fx["dts"][0])
     out = run_stage(lib_default, fx, nt=nt, tys=tys, coef=coef)
     check(fx, *out, coef)
+
+
+def _tile_cover(lib, nx, ny, nt, tys, ns, ew):
+    """cells each launch of plan_tiles writes, as the stage kernel maps them (pyh_stage_march.cuh: output columns
+    bx * (nt - 4) .. + nt - 5 of strip bx, rows [row0 + by * rowstride, min(+ tys, row1)))"""
+    out = (C.c_int * 27)()
+    n = lib.twin_plan_tiles(nx, ny, nt, tys, int(ns), int(ew), out)
+    cover = np.zeros((ny, nx), dtype=np.int32)
+    edge = np.zeros((ny, nx), dtype=bool)
+    for q in range(n):
+        row0, rowstride, row1, xfirst, xstride, gx, gy, t_, is_edge = out[9 * q: 9 * q + 9]
+        for by in range(gy):
+            i0 = row0 + by * rowstride
+            i1 = min(i0 + t_, row1)
+            for x in range(gx):
+                bx = xfirst + x * xstride
+                j0, j1 = bx * (nt - 4), min(bx * (nt - 4) + nt - 4, nx)
+                cover[i0:i1, j0:j1] += 1
+                if is_edge:
+                    edge[i0:i1, j0:j1] = True
+    return n, cover, edge
+
+
+@pytest.mark.parametrize("nx,ny,nt,tys", [(2048, 2048, 128, 64), (150, 150, 160, 3), (26, 22, 64, 4), (26, 22, 32, 4), (500, 500, 64, 16),
+                                          (36, 6, 16, 4), (24, 8, 12, 3), (300, 9, 32, 2), (1080, 60, 128, 16), (7, 40, 64, 64)])
+@pytest.mark.parametrize("ns,ew", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_tile_plan_covers_every_cell_once_and_edges_precede_the_exchange(lib_default, nx, ny, nt, tys, ns, ew):
+    """Invariants of pyh_plan.cuh: plan_tiles for every shape the chooser can pick: (1) the launches of a stage write every cell
+    exactly once; (2) every cell a remote neighbour needs -- first / last row with north / south neighbours on other ranks,
+    first / last column with east / west ones -- is written by an EDGE launch, because the strip exchange is enqueued right
+    behind the edge launches (round 2: the 8-rank run caught a plan that left the east / west columns of a block too narrow to
+    split in the interior launch)."""
+    n, cover, edge = _tile_cover(lib_default, nx, ny, nt, tys, ns, ew)
+    assert 1 <= n <= 3
+    assert (cover == 1).all(), (n, np.argwhere(cover != 1)[:5])
+    if ns:
+        assert edge[0, :].all() and edge[-1, :].all()
+    if ew:
+        assert edge[:, 0].all() and edge[:, -1].all()
+    if not ns and not ew:
+        assert n == 1 and edge.all()       # single rank: one launch, nothing to overlap

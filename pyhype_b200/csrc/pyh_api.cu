@@ -84,6 +84,7 @@ struct Ctx {
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
     int march_nt = 128, march_tys = 64;
     bool march_configured = false;   // cudaFuncSetAttribute done for this context's device
+    bool push_ok = false;            // ghost cells are written by the stage kernel itself (plan.push_ghost): no k_ghost / k_pack_halo per stage
     // asynchronous state streaming (pyh_upload_state_async & co)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in_done = nullptr, ev_in_consumed = nullptr, ev_out_ready = nullptr;
@@ -261,6 +262,7 @@ StagePlan advance_roles(Ctx* c, int s, bool fuse_dt = false) {
     const int next = plan_next_buffer(S, s, cur, c->i0, c->i1, c->i2);
     StagePlan p = make_plan(c, s, cur, next);
     p.fuse_dt = (fuse_dt && s == S - 1) ? 1 : 0;   // the last stage also reduces the CFL minimum of the state it writes
+    p.push_ghost = c->push_ok ? 1 : 0;             // ... and every stage refreshes the ghost cells that mirror the edge cells it writes
     c->cur = next;
     if (s == S - 1) {
         if (S == 1) std::swap(c->i0, c->i1);
@@ -291,22 +293,25 @@ int launch_dt(Ctx* c, int buf, int respect_active = 0) {
 // Remote ghost strips of buffer `buf` (GhostBlock.send_boundary_data / recieve_boundary_data / apply_recv_buffers_to_state,
 // blocks/ghost.py:169-241, and the Waitall of blocks/base.py:454-465): pack the edge strips the neighbour ranks need, ONE
 // grouped ncclSend / ncclRecv batch, unpack into the ghost frames -- all in order on the compute stream (capturable).
-int exchange_halo(Ctx* c, int buf, cudaStream_t st = nullptr) {
+int exchange_halo(Ctx* c, int buf, cudaStream_t st = nullptr, bool packed = false) {
     Comm& m = c->comm;
     if (!st) st = c->stream;
     if (!m.comm || c->slots.empty()) return 0;
     NcclApi& N = nccl_api();
     const int mx = std::max(c->lay.nx, c->lay.ny);
     dim3 grid(cdiv(mx, 128), (unsigned)c->slots.size());
-    k_pack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_send);
-    CU(cudaGetLastError());
+    if (!packed) {   // after a stage with plan.push_ghost the stage kernel has already written the strips into the send buffer
+        k_pack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_send);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
     NC(N.GroupStart());
     for (const HaloMsg& r : m.recvs) NC(N.Recv(m.d_recv + r.offset, (size_t)r.len, kNcclFloat64, r.peer, m.comm, st));
     for (const HaloMsg& q : m.sends) NC(N.Send(m.d_send + q.offset, (size_t)q.len, kNcclFloat64, q.peer, m.comm, st));
     NC(N.GroupEnd());
     k_unpack_halo<<<grid, 128, 0, st>>>(c->d_blks, c->lay, c->po.H[buf], c->d_slots, m.d_recv);
     CU(cudaGetLastError());
-    c->launches += 2;
+    c->launches++;
     return 0;
 }
 
@@ -330,8 +335,8 @@ int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
     }
     if (!force_split && (!c->comm.comm || c->slots.empty() || no_overlap || !c->s_edge)) {
         if ((rc = launch_stage(c, p, 0))) return rc;
-        if ((rc = exchange_halo(c, c->cur))) return rc;
-        return do_ghost(c, c->cur);
+        if ((rc = exchange_halo(c, c->cur, nullptr, c->push_ok))) return rc;
+        return c->push_ok ? 0 : do_ghost(c, c->cur);
     }
     TileLaunch tl[3];
     static const int edge_rows = getenv("PYH_EDGE_ROWS") ? std::max(1, atoi(getenv("PYH_EDGE_ROWS"))) : kEdgeRows;   // diagnostics
@@ -340,12 +345,12 @@ int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
     CU(cudaStreamWaitEvent(c->s_edge, c->ev_fork, 0));
     for (int q = 0; q < n; ++q)
         if (tl[q].edge && (rc = launch_stage(c, p, 0, tl[q], c->s_edge))) return rc;
-    if ((rc = exchange_halo(c, c->cur, c->s_edge))) return rc;
+    if ((rc = exchange_halo(c, c->cur, c->s_edge, c->push_ok))) return rc;
     CU(cudaEventRecord(c->ev_edge_done, c->s_edge));
     for (int q = 0; q < n; ++q)
         if (!tl[q].edge && (rc = launch_stage(c, p, 0, tl[q], c->stream))) return rc;
     CU(cudaStreamWaitEvent(c->stream, c->ev_edge_done, 0));
-    return do_ghost(c, c->cur);
+    return c->push_ok ? 0 : do_ghost(c, c->cur);   // local ghost cells: written by the stage kernel itself, else by k_ghost
 }
 
 // Global CFL minimum and realizability flag (Solver.get_dt gathers and broadcasts the minimum, solvers/base.py:128-131;
@@ -538,6 +543,27 @@ int pyh_finalize(void* ctx) {
                 c->halo_doubles += 4LL * len;
             }
         }
+    }
+    // Push-model ghost refresh (pyh_stage_march.cuh: push_ghost_cells) needs a symmetric topology: where block b sees block n
+    // across side s without a boundary condition, n must see b across the opposite side without one.  Every mesh generator
+    // of the reference builds such dictionaries; anything else keeps the per-stage k_ghost / k_pack_halo kernels.
+    {
+        static const int opposite[4] = {PYH_WEST, PYH_EAST, PYH_SOUTH, PYH_NORTH};
+        bool sym = getenv("PYH_NO_PUSH_GHOST") == nullptr;
+        for (auto& hb : c->blocks)
+            for (int s = 0; s < 4 && sym; ++s) {
+                if (hb.dev.nbr[s] < 0 || hb.d.bc[s] != PYH_BC_NONE) continue;
+                const HostBlock& nb = c->blocks[hb.dev.nbr[s]];
+                sym = nb.d.bc[opposite[s]] == PYH_BC_NONE && nb.d.neighbor[opposite[s]] == hb.d.gid && nb.d.neighbor_is_local[opposite[s]];
+            }
+        c->push_ok = sym;
+    }
+    if (c->halo_doubles > 0) {   // strips for / from neighbours on other ranks (also the target of the stage kernel's pushes)
+        CU(cudaMalloc(&c->comm.d_send, (size_t)c->halo_doubles * sizeof(double)));
+        CU(cudaMalloc(&c->comm.d_recv, (size_t)c->halo_doubles * sizeof(double)));
+        CU(cudaMemset(c->comm.d_send, 0, (size_t)c->halo_doubles * sizeof(double)));
+        c->comm.doubles = c->halo_doubles;
+        for (const HaloSlot& hs : c->slots) c->blocks[hs.blk].dev.send[hs.side] = c->comm.d_send + hs.offset;
     }
     std::vector<BlkDev> tmp;
     for (auto& hb : c->blocks) tmp.push_back(hb.dev);
@@ -917,9 +943,13 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         CU(cudaGetLastError());
         for (int s = 0; s < c->cfg.num_stages; ++s)
             if ((r = stage_and_refresh(c, s, !no_fuse))) return r;
+        c->launches += 1;   // k_dt_finalize: the step boundary (end of the previous step + dt / stop test of this one)
+        return 0;
+    };
+    auto flush_step_end = [&]() -> int {   // the end of the last enqueued step, before the host looks at t / nsteps
         k_step_end<<<1, 1, 0, c->stream>>>(c->d_ctl);
         CU(cudaGetLastError());
-        c->launches += 2;
+        c->launches += 1;
         return 0;
     };
     if (!no_fuse && (rc = launch_dt(c, c->i0, 0))) return rc;   // CFL minimum of the state the call starts from
@@ -963,6 +993,7 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
         for (; n < chunk; ++n) if ((rc = enqueue_step())) return rc;
         issued += chunk;
         enqueued += chunk;
+        if ((rc = flush_step_end())) return rc;
         CU(cudaMemcpyAsync(&h, c->d_ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (!h.active || h.bad || !(h.t < h.t_final)) break;
@@ -1130,11 +1161,7 @@ int pyh_comm_init(void* ctx, int32_t rank, int32_t world, const void* id, const 
     }
     std::sort(m.sends.begin(), m.sends.end(), msg_less);
     std::sort(m.recvs.begin(), m.recvs.end(), msg_less);
-    m.doubles = c->halo_doubles;
-    if (m.doubles > 0) {
-        CU(cudaMalloc(&m.d_send, (size_t)m.doubles * sizeof(double)));
-        CU(cudaMalloc(&m.d_recv, (size_t)m.doubles * sizeof(double)));
-    }
+    m.doubles = c->halo_doubles;   // send / receive buffers: allocated by pyh_finalize
     NcclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
     NC(N.CommInitRank(&m.comm, world, uid, rank));

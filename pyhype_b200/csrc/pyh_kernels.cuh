@@ -161,9 +161,20 @@ k_dt(const BlkDev* __restrict__ blks, Layout lay, PlaneOffsets po, unsigned buf,
     }
 }
 
-// mode 0: device-resident loop (Solver.get_dt clamp + while t < t_final)
+// end of a step (Euler2D.py:209-210): t += dt, step counter, optional dt record
+__device__ __forceinline__ void apply_step_end(Control* ctl) {
+    if (!ctl->pending_end) return;
+    ctl->pending_end = 0;
+    if (ctl->dts && ctl->nsteps < ctl->dts_cap) ctl->dts[ctl->nsteps] = ctl->dt;
+    ctl->t += ctl->dt;
+    ctl->nsteps += 1;
+}
+
+// mode 0: one STEP BOUNDARY of the device-resident loop: the end of the previous step (if one ran), then Solver.get_dt's clamp
+//         and the `while t < t_final` test for the next one
 // mode 1: write CFL*min to *out only (pyh_local_dt / pyh_get_dt)
 __global__ void k_dt_finalize(Control* ctl, double cfl, Tableau tab, int mode, double* out) {
+    if (mode == 0) apply_step_end(ctl);
     double dt = cfl * dunkey(ctl->dtmin_bits);      // quad_block.py:436 ; min over blocks (and ranks) is exact
     ctl->dtmin_bits = DKEY_INF;
     if (!ctl->allok) ctl->bad = 1;                  // a rank saw an unrealizable state (Euler2D.py:144-152 aborts every rank)
@@ -175,6 +186,7 @@ __global__ void k_dt_finalize(Control* ctl, double cfl, Tableau tab, int mode, d
     double rem = ctl->t_final - ctl->t;             // solvers/base.py:132-136
     dt = rem < dt ? rem : dt;
     ctl->dt = dt;
+    ctl->pending_end = 1;                           // the stages that follow are this step; its end is applied at the next boundary
     for (int s = 0; s < tab.nstages; ++s)
         for (int k = 0; k <= s; ++k)
             ctl->coef[s * PYH_MAX_STAGES + k] = dt * tab.a[s * PYH_MAX_STAGES + k];   // explicit_runge_kutta.py:71
@@ -189,12 +201,8 @@ __global__ void k_set_dt(Control* ctl, double dt_host, const double* dt_dev, Tab
             ctl->coef[s * PYH_MAX_STAGES + k] = dt * tab.a[s * PYH_MAX_STAGES + k];
 }
 
-__global__ void k_step_end(Control* ctl) {
-    if (!ctl->active) return;
-    if (ctl->dts && ctl->nsteps < ctl->dts_cap) ctl->dts[ctl->nsteps] = ctl->dt;
-    ctl->t += ctl->dt;                               // Euler2D.py:209-210
-    ctl->nsteps += 1;
-}
+// the end of the LAST enqueued step (before the host reads the control block)
+__global__ void k_step_end(Control* ctl) { apply_step_end(ctl); }
 
 // ------------------------------------------------------------------------------------------------
 // setup: derived geometry from node coordinates (exact IEEE restatement of mesh/base.py:57-64,

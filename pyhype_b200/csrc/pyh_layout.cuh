@@ -49,6 +49,7 @@ struct StagePlan {
     int ntargets;
     int write_residual;   // test hook: also store R itself into BlkDev::dbg
     int fuse_dt;          // last stage of a step inside pyh_run: CFL minimum + realizability of the NEW state (the next step's dt)
+    int push_ghost;       // the thread that writes an edge cell of the stage's output also writes the ghost cells that mirror it
     unsigned cur;         // slab offset of the state buffer this stage reads
     RkTarget t[PYH_MAX_STAGES];
 };
@@ -63,7 +64,8 @@ struct Control {
     long long nsteps;
     int active;      // 1 while t < t_final
     int bad;         // unrealizable state seen
-    int pad[2];
+    int pending_end; // a step has run whose `t += dt` is still to be applied (k_dt_finalize / k_step_end do it: one kernel per step boundary)
+    int pad;
     double* dts;                     // pyh_run: optional per-step dt record (device), dts_cap entries
     long long dts_cap;
 };
@@ -89,6 +91,7 @@ struct BlkDev {
     int bc[4];
     int nbr[4];                   // local block index of the neighbour or -1
     int remote_slot[4];           // halo slot (>= 0) when the neighbour is on another rank
+    double* send[4];              // where this block's edge strip for a remote neighbour goes (pyh_comm_init), (edge_len, 4) doubles
     int cart;
     int gid;
 };

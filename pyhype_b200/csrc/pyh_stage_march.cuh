@@ -59,6 +59,49 @@ static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t str
 #endif
 #define PYH_ROS(expr) PYH_RO(expr)
 
+// Ghost refresh at the source (Blocks.apply_boundary_condition, blocks/base.py:448-471, GhostBlock.* blocks/ghost.py:187-278, as
+// a PUSH): the thread that has just written cell (i, j) of the stage's output -- a cell on the edge of its block -- also
+// writes every ghost cell that mirrors it: the neighbour block's ghost frame (same GPU), the block's own ghost frame through
+// the boundary-condition functor (reflection / slip wall, outlet copy, Dirichlet inlet), or the send buffer of a neighbour
+// on another rank.  Same values, same arithmetic (`reflect`) as k_ghost / k_pack_halo, which remain for the refresh after an
+// upload; what disappears is one kernel launch per stage (and the pack launch before every NCCL exchange).  Out of line: 1
+// cell in 512 takes it at the benchmark size.
+static __device__ __noinline__ void push_ghost_cells(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
+                                                     const unsigned dst, const int i, const int j, const double u0, const double u1,
+                                                     const double u2, const double u3) {
+    const int nx = lay.nx, ny = lay.ny;
+    const unsigned PL = lay.plane;
+#pragma unroll 1
+    for (int side = 0; side < 4; ++side) {
+        int gi, gj, oi, oj, fi, fj, idx;      // own ghost cell, the neighbour's mirror ghost cell, the boundary face, index along the edge
+        if (side == PYH_EAST)       { if (j != nx - 1) continue; idx = i; gi = i; gj = nx; oi = i; oj = -1; fi = i; fj = nx; }
+        else if (side == PYH_WEST)  { if (j != 0) continue;      idx = i; gi = i; gj = -1; oi = i; oj = nx; fi = i; fj = 0; }
+        else if (side == PYH_NORTH) { if (i != ny - 1) continue; idx = j; gi = ny; gj = j; oi = -1; oj = j; fi = ny; fj = j; }
+        else                        { if (i != 0) continue;      idx = j; gi = -1; gj = j; oi = ny; oj = j; fi = 0;  fj = j; }
+        const int bc = B.bc[side];
+        double q0 = u0, q1 = u1, q2 = u2, q3 = u3;
+        if (bc != PYH_BC_NONE || (B.nbr[side] < 0 && B.remote_slot[side] < 0)) {      // the block's own ghost strip (+ BC functor)
+            if (bc == PYH_BC_REFLECTION || bc == PYH_BC_SLIPWALL) {
+                const unsigned of = lay.at(fi, fj);
+                const bool vert = (side == PYH_EAST || side == PYH_WEST);
+                const double c_ = B.base[(vert ? po.cv : po.ch) + of], s_ = B.base[(vert ? po.sv : po.sh) + of];
+                reflect(q1, q2, c_, s_);
+            } else if (bc == PYH_BC_PRIMITIVE_DIRICHLET) {
+                const double* d = B.dir_cons[side] + 4 * (long long)idx;
+                q0 = d[0]; q1 = d[1]; q2 = d[2]; q3 = d[3];
+            }
+            double* g = B.base + dst + lay.at(gi, gj);
+            g[0] = q0; g[PL] = q1; g[2 * PL] = q2; g[3 * PL] = q3;
+        } else if (B.nbr[side] >= 0) {                                                  // neighbour on this GPU: its ghost frame
+            double* g = blks[B.nbr[side]].base + dst + lay.at(oi, oj);
+            g[0] = q0; g[PL] = q1; g[2 * PL] = q2; g[3 * PL] = q3;
+        } else {                                                                        // neighbour on another rank: the send buffer
+            double* g = B.send[side] + 4 * (long long)idx;
+            g[0] = q0; g[1] = q1; g[2] = q2; g[3] = q3;
+        }
+    }
+}
+
 typedef std::integral_constant<bool, true> FastTag;
 typedef std::integral_constant<bool, false> SafeTag;
 
@@ -457,6 +500,8 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         double un[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { un[k] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k]; base[plan.t[0].dst + k * PL + om] = un[k]; }
+                        if (plan.push_ghost && (r - 1 == 0 || r == ny || j == 0 || j == nx - 1))      // an edge cell of the block (target 0 is the stage's output state)
+                            push_ghost_cells(blks, B, lay, po, plan.t[0].dst, r - 1, j, un[0], un[1], un[2], un[3]);
                         if (plan.fuse_dt) {
                             // QuadBlock.get_dt (quad_block.py:423-436) + the realizability conditions (states/conservative.py:161-165) on
                             // the state this step ends with, which is still in registers: the next step's Solver.get_dt costs no pass

@@ -224,16 +224,21 @@ int twin_steps(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, in
     for (int n = 0; n < nsteps; ++n) {
         for (int s = 0; s < S; ++s)            // k_set_dt (explicit_runge_kutta.py:71: dt * a[s][k] formed first)
             for (int k = 0; k <= s; ++k) T.ctl.coef[s * PYH_MAX_STAGES + k] = dts[n] * tab[s * PYH_MAX_STAGES + k];
+        // ghost refresh: by the stage kernel itself (plan.push_ghost, the product's default) on even steps, by k_ghost behind
+        // the stage (topologies the push cannot serve, PYH_NO_PUSH_GHOST) on odd steps -- both must give the reference's state
+        const bool push = getenv("PYH_TWIN_NO_PUSH") ? false : (n % 2 == 0);
         for (int s = 0; s < S; ++s) {          // do_stage + do_ghost
             cur = (s == 0) ? i0 : cur;
             const int next = plan_next_buffer(S, s, cur, i0, i1, i2);
-            T.stage(plan_stage(tab, S, T.po, i0, s, cur, next), 0);
+            StagePlan pl = plan_stage(tab, S, T.po, i0, s, cur, next);
+            pl.push_ghost = push ? 1 : 0;
+            T.stage(pl, 0);
             cur = next;
             if (s == S - 1) {
                 if (S == 1) std::swap(i0, i1);
                 cur = i0;
             }
-            T.ghost(cur);
+            if (!push) T.ghost(cur);
         }
     }
     T.fetch_state(i0, Uout);
@@ -274,15 +279,15 @@ int twin_run(int flux, int lim, int prim, int nq, int nx, int ny, int nblk, int 
             const int next = plan_next_buffer(S, s, cur, i0, i1, i2);
             StagePlan pl = plan_stage(tab, S, T.po, i0, s, cur, next);
             pl.fuse_dt = (s == S - 1) ? 1 : 0;
+            pl.push_ghost = 1;                            // no k_ghost between the stages: the stage kernel refreshes the frames
             T.stage(pl, 0);
             cur = next;
             if (s == S - 1) {
                 if (S == 1) std::swap(i0, i1);
                 cur = i0;
             }
-            T.ghost(cur);
         }
-        k_step_end(&ctl);
+        k_step_end(&ctl);                                 // (the product flushes the step end only before it polls: same arithmetic)
         if (!ctl.active || ctl.bad || !(ctl.t < ctl.t_final)) break;
     }
     double tmp = 0.0;                                     // final realizability check: the flag the last step reduced

@@ -60,19 +60,21 @@ static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t str
 #define PYH_ROS(expr) PYH_RO(expr)
 
 // Ghost refresh at the source (Blocks.apply_boundary_condition, blocks/base.py:448-471, GhostBlock.* blocks/ghost.py:187-278, as
-// a PUSH): the thread that has just written cell (i, j) of the stage's output -- a cell on the edge of its block -- also
-// writes every ghost cell that mirrors it: the neighbour block's ghost frame (same GPU), the block's own ghost frame through
-// the boundary-condition functor (reflection / slip wall, outlet copy, Dirichlet inlet), or the send buffer of a neighbour
-// on another rank.  Same values, same arithmetic (`reflect`) as k_ghost / k_pack_halo, which remain for the refresh after an
-// upload; what disappears is one kernel launch per stage (and the pack launch before every NCCL exchange).  Out of line: 1
-// cell in 512 takes it at the benchmark size.
-static __device__ __noinline__ void push_ghost_cells(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
-                                                     const unsigned dst, const int i, const int j, const double u0, const double u1,
-                                                     const double u2, const double u3) {
+// a PUSH): a thread block that has written cells on the edge of its mesh block also writes, at its very end, every ghost cell
+// that mirrors them: the neighbour block's ghost frame (same GPU), the block's own ghost frame through the boundary-condition
+// functor (reflection / slip wall, outlet copy, Dirichlet inlet), or the send buffer of a neighbour on another rank.  Same
+// values, same arithmetic (`reflect`) as k_ghost / k_pack_halo, which remain for the refresh after an upload; what disappears
+// is one kernel launch per stage (and the pack launch before every NCCL exchange).  Cell (i, j) of the stage's output
+// buffer `dst`, sides selected by `ns` (north / south) or east / west.  (Called from the tail of the kernel: a call inside
+// the row loop, however rarely taken, cost the loop 12 % through the registers it pinned -- measured.)
+static __device__ __forceinline__ void push_ghost_cell(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
+                                                       const unsigned dst, const int i, const int j, const bool ns) {
     const int nx = lay.nx, ny = lay.ny;
     const unsigned PL = lay.plane;
+    const double* u = B.base + dst + lay.at(i, j);
+    const double u0 = u[0], u1 = u[PL], u2 = u[2 * PL], u3 = u[3 * PL];
 #pragma unroll 1
-    for (int side = 0; side < 4; ++side) {
+    for (int side = ns ? PYH_NORTH : PYH_EAST; side <= (ns ? PYH_SOUTH : PYH_WEST); ++side) {
         int gi, gj, oi, oj, fi, fj, idx;      // own ghost cell, the neighbour's mirror ghost cell, the boundary face, index along the edge
         if (side == PYH_EAST)       { if (j != nx - 1) continue; idx = i; gi = i; gj = nx; oi = i; oj = -1; fi = i; fj = nx; }
         else if (side == PYH_WEST)  { if (j != 0) continue;      idx = i; gi = i; gj = -1; oi = i; oj = nx; fi = i; fj = 0; }
@@ -500,8 +502,6 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         double un[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { un[k] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k]; base[plan.t[0].dst + k * PL + om] = un[k]; }
-                        if (plan.push_ghost && (r - 1 == 0 || r == ny || j == 0 || j == nx - 1))      // an edge cell of the block (target 0 is the stage's output state)
-                            push_ghost_cells(blks, B, lay, po, plan.t[0].dst, r - 1, j, un[0], un[1], un[2], un[3]);
                         if (plan.fuse_dt) {
                             // QuadBlock.get_dt (quad_block.py:423-436) + the realizability conditions (states/conservative.py:161-165) on
                             // the state this step ends with, which is still in registers: the next step's Solver.get_dt costs no pass
@@ -562,6 +562,24 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
             const double m = sDT[0];
             if (m == __longlong_as_double(0xfff0000000000000ll)) { atomicOr(&ctl_out->bad, 1); atomicExch(&ctl_out->allok, 0ull); }
             else atomicMin(&ctl_out->dtmin_bits, dkey(m));
+        }
+    }
+    if (plan.push_ghost && plan.ntargets > 0) {
+        // ghost cells mirroring the block-edge cells this thread block has written (target 0 is the stage's output state)
+        const int jlo = (int)bx * (NT - 4), jhi = min(jlo + NT - 4, nx);      // its output columns
+        const bool rowS = (i0 == 0) && (i1 > 0), rowN = (i1 == ny) && (i1 > i0);
+        const bool colW = (jlo == 0), colE = (jhi == nx);
+        if ((rowS || rowN || colW || colE) && (i1 > i0)) {
+            __syncthreads();      // the stores of the whole thread block are visible to each of its threads
+            const unsigned dst = plan.t[0].dst;
+            if (outcol) {
+                if (rowS) push_ghost_cell(blks, B, lay, po, dst, 0, j, true);
+                if (rowN && !(rowS && ny == 1)) push_ghost_cell(blks, B, lay, po, dst, ny - 1, j, true);
+            }
+            for (int i = i0 + t; i < i1; i += NT) {
+                if (colW) push_ghost_cell(blks, B, lay, po, dst, i, 0, false);
+                if (colE && !(colW && nx == 1)) push_ghost_cell(blks, B, lay, po, dst, i, nx - 1, false);
+            }
         }
     }
 }

@@ -54,6 +54,20 @@ CASES = {
     "ws2048": dict(mesh="ws_mesh", mesh_args=(1, 1), ic="ws_ic_1x1", nx=2048, ny=2048, stride=64, checkpoints=[1], by_oracle=True,
                    cfg=dict(t_final=0.07),
                    what="synthetic weak-scaling explosion at the headline block size: one block of 2048 x 2048, first RK4 step, by the numpy oracle"),
+    # the remaining shipped examples at their shipped sizes (single-block problems are renumbered to block 0)
+    "explosion": dict(mesh="em_mesh", mesh_args=(1, 1), ic="explosion_ic", nx=40, ny=40, stride=4, checkpoints=[50, -1],
+                      cfg=dict(t_final=0.07),
+                      what="examples/explosion as shipped (one 40 x 40 block, Roe, RK4, CFL 0.7), initial condition -> t_final"),
+    "implosion": dict(mesh="em_mesh", mesh_args=(1, 1, 10.0, 10.0), ic="implosion_ic", nx=40, ny=40, stride=4, checkpoints=[100, -1],
+                      cfg=dict(time_integrator="RK2", CFL=0.4, t_final=0.1),
+                      what="examples/implosion as shipped (one 40 x 40 block, Roe, RK2, CFL 0.4), initial condition -> t_final"),
+    "shockbox": dict(mesh="em_mesh", mesh_args=(1, 1, 10.0, 10.0), ic="shockbox_ic", nx=50, ny=50, stride=5, checkpoints=[10, 23], aborts_next=True,
+                     cfg=dict(time_integrator="RK2", CFL=0.4, t_final=2.0),
+                     what="examples/shockbox as shipped (one 50 x 50 block, Roe, RK2, CFL 0.4): the reference's own run stops with an unrealizable "
+                          "state in step 24, so the fingerprint holds steps 10, 23 and the abort"),
+    "step": dict(mesh="step_mesh", mesh_args=(64,), ic="step_ic", nx=192, ny=64, stride=16, checkpoints=[10, 100],
+                 cfg=dict(fvm_flux_function_type="HLLL", time_integrator="RK2", CFL=0.3, reconstruction_type="primitive", t_final=20.0),
+                 what="examples/supersonic_step as shipped (ten 192 x 64 blocks, Mach 5 Dirichlet inlet, HLLL, primitive reconstruction, RK2, CFL 0.3), first 100 steps"),
     # BASELINE.json configs[2]: examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall,
     # 15 degree ramp), with the shipped flux (HLLL) and with the one BASELINE.json names (Roe); first 50 steps
     "wedge": dict(mesh="wedge_mesh", mesh_args=(60,), ic="wedge_ic", nx=60, ny=60, stride=6, checkpoints=[10, 50],

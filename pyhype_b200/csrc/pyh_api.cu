@@ -194,6 +194,19 @@ void choose_march_shape(Ctx* c) {
         tys = std::max(4, std::min(tys, cap));
     }
     auto n_ctas = [&](int n, int ty) { return (long long)((nx + n - 5) / (n - 4)) * nblk * ((ny + ty - 1) / ty); };
+    if (tys == 64 && ny > 100) {
+        // large problem: rows per strip near 64 such that the thread blocks fill an integer number of waves (8 x 2048^2: 79
+        // rows = 5.97 waves of 592 instead of 64 rows = 7.35; measured -1 %, profiles/r02m_rows_per_strip.txt)
+        const long long slots = slots_for(nt);
+        double best_cost = 1e300;
+        int best_ty = tys;
+        for (int ty = 48; ty <= std::min(ny, 100); ++ty) {
+            const long long ctas = n_ctas(nt, ty);
+            const double cost = (double)((ctas + slots - 1) / slots) * (ty + 1.05) + 1e-3 * std::abs(ty - 64);
+            if (cost < best_cost) { best_cost = cost; best_ty = ty; }
+        }
+        tys = best_ty;
+    }
     if (n_ctas(nt, tys) <= 3 * slots_for(nt)) {   // small problem: cheapest (nt, tys) by the wave model
         double best_cost = 1e300;
         for (int n : cand) {

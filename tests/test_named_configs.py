@@ -4,6 +4,10 @@
 * the weak-scaling block of bench.py: one block of 1024 x 1024 against the unmodified reference (the largest its object model
   fits in the build container), first 2 RK4 steps; and the headline size itself, one block of 2048 x 2048, first step, against the
   numpy restatement (`ws2048`, labelled so in its metadata);
+* the remaining shipped examples at their shipped sizes: explosion (one 40 x 40 block) and implosion (40 x 40, RK2) from the initial
+  condition to t_final, shockbox (50 x 50, RK2) up to the abort the reference itself raises in step 24, supersonic_step (ten 192 x 64
+  blocks of an irregular topology, Mach 5 Dirichlet inlet, HLLL) for 100 steps: with these EVERY example the reference ships is
+  replayed at the size it ships with;
 * examples/supersonic_wedge at its shipped size (2 blocks of 60 x 60, Dirichlet inlet, reflection wall, 15 degree ramp), with
   the shipped HLLL flux and with the Roe flux BASELINE.json names, first 50 steps;
 * examples/jet at its shipped size (9 stacked blocks of 1080 x 60, slip walls + Dirichlet inlet), shipped HLLL flux, first 50
@@ -78,7 +82,7 @@ class Named:
             assert value_digest(U) == self.meta["digests"][f"{n}_{g}"], (self.name, n, g, np.abs(sub - ref).max())
 
 
-ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle", "ws1024", "ws2048"]
+ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle", "ws1024", "ws2048", "explosion", "implosion", "shockbox", "step"]
 
 
 @pytest.mark.gpu

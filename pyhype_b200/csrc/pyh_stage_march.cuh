@@ -295,7 +295,7 @@ k_stage_march(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
                         else
 #endif
                         if (!limiter4_fast<LIM>(dmx, dmn, davg, pp)) limiter4_safe<LIM>(dmx, dmn, davg, pp);
-                        phi = (p == 0) ? pp : dmin2(phi, pp);
+                        phi = (p == 0) ? pp : dmin2_nan(phi, pp);
                     }
                     if (phi < 0.0) phi = 0.0;                                         // limiters/base.py:187
 #pragma unroll

@@ -141,3 +141,23 @@ def test_stage_kernel_source_twin_at_named_size_first_checkpoint(name):
     assert nsteps == n and not bad
     assert np.array_equal(dts, fp.dts[:n])
     fp.check(n, {g: Uout[idx[g]] for g in fp.gids})
+
+
+def test_stage_kernel_source_twin_reports_the_abort_of_shockbox():
+    """examples/shockbox: in step 24 a slope of 1.4e211 overflows the Venkatakrishnan quotient to inf / inf; np.minimum.reduce
+    (limiters/base.py:179-186) carries the NaN into phi, four cells of the state turn NaN and the reference aborts
+    (Euler2D.py:144-152).  The kernel source must produce the same NaN cells in the same step (its minimum over the faces
+    is NaN-propagating for exactly this reason) and raise the flag; found by the first GPU run of the shockbox fingerprint."""
+    import test_kernel_twin as T
+
+    fp = Named("shockbox")
+    n = fp.meta["aborts_in_step"]
+    idx, Uout, dts, t, nsteps, bad = T.run_loop(T.build("default"), fp, 0.0, fp.meta["t_final_nd"], n + 2, nt=64, tys=16)
+    assert bad and nsteps == n
+    assert np.array_equal(dts[: n - 1], fp.dts[: n - 1])
+    prob = cases.build_oracle(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
+    with pytest.raises(RuntimeError, match="unrealizable"):
+        prob.run(0.0, fp.meta["t_final_nd"], max_steps=n)
+    g = fp.gids[0]
+    assert np.isnan(prob.blocks[g].U).sum() == 16 and not prob.realizable()
+    assert np.array_equal(Uout[idx[g]], prob.blocks[g].U, equal_nan=True)

@@ -306,3 +306,79 @@ def test_limiter_fast_path_is_sound_for_any_magnitude(twin, lim):
             assert len(bad) == 0, (lim, kq, kt, len(bad), dmx[bad[:1]], dmn[bad[:1]], davg[bad[:1]], phi[bad[:1]], ref[bad[:1]])
             accepted += int((ok & fin).sum())
     assert accepted > n * 20
+
+
+@pytest.mark.parametrize("lim", ["Venkatakrishnan", "VanLeer", "VanAlbada", "BarthJespersen"])
+def test_limiter_as_the_kernel_evaluates_it_matches_numpy_including_nan(twin, lim):
+    """What the stage kernel does -- the fast pass, and the plain-operator pass where the fast one declines -- against numpy for
+    ANY finite operands, NaN results included: an overflowing slope turns the Venkatakrishnan / VanAlbada quotient into
+    inf / inf, np.minimum.reduce (limiters/base.py:179-186) carries the NaN into phi, and the reference's run ends there
+    (examples/shockbox, step 24).  A minimum that drops the NaN keeps running on a state the reference never had."""
+    rng = np.random.default_rng(43)
+    n = 4000
+    lid = ["Venkatakrishnan", "VanLeer", "VanAlbada", "BarthJespersen"].index(lim)
+    nans = 0
+    for kq in SCALES:
+        for kt in (-600, -300, -120, -30, 0, 30, 120, 300, 600):
+            with np.errstate(all="ignore"):
+                q = rng.uniform(-2, 2, n) * 2.0**kq
+                nb = q[:, None] * (1.0 + rng.standard_normal((n, 4)) * rng.choice([1e-12, 1e-6, 1e-2, 1.0], (n, 1)))
+                mx = np.maximum(q, nb.max(axis=1))
+                mn = np.minimum(q, nb.min(axis=1))
+                dmx, dmn = mx - q, mn - q
+                term = rng.standard_normal((n, 4)) * rng.choice([0.0, 1e-9, 1e-3, 0.5], (n, 4)) * np.ldexp(1.0, max(-1070, min(1020, kq + kt)))
+                if kt == 0 and kq <= -400:
+                    # a variable that is (still) noise next to neighbours of order one, like the y momentum ahead of shockbox's fronts
+                    nb = rng.uniform(-2, 2, (n, 4))
+                    mx = np.maximum(q, nb.max(axis=1))
+                    mn = np.minimum(q, nb.min(axis=1))
+                    dmx, dmn = mx - q, mn - q
+                    term = rng.standard_normal((n, 4)) * np.ldexp(1.0, kq + rng.integers(0, 40, (n, 4)))
+                davg = (q[:, None] + term) - q[:, None]
+                slope = np.where(davg > 0, dmx[:, None] / davg, np.where(davg < 0, dmn[:, None] / davg, 1.0))
+                ref = np.minimum.reduce(tuple(mo.LIMITERS[lim](slope[:, f]) for f in range(4)))
+            fin = np.isfinite(dmx) & np.isfinite(dmn) & np.all(np.isfinite(davg), axis=1)
+            dmx, dmn = np.ascontiguousarray(dmx), np.ascontiguousarray(dmn)
+            pf, okf = twin.limiter4(lid, 1, dmx, dmn, davg)
+            ps, _ = twin.limiter4(lid, 0, dmx, dmn, davg)
+            phi = np.where(okf, pf, ps)
+            good = (phi == ref) | (np.isnan(phi) & np.isnan(ref))
+            bad = np.nonzero(fin & ~good)[0]
+            assert len(bad) == 0, (lim, kq, kt, len(bad), dmx[bad[:1]], dmn[bad[:1]], davg[bad[:1]], phi[bad[:1]], ref[bad[:1]])
+            nans += int((fin & np.isnan(ref)).sum())
+    if lim in ("Venkatakrishnan", "VanAlbada"):
+        assert nans > 100      # the sweep does reach the overflow
+
+
+@pytest.mark.parametrize("flux", ["Roe", "HLLE", "HLLL"])
+@pytest.mark.parametrize("prim", [0, 1], ids=["conservative", "primitive"])
+def test_riemann_solvers_on_unrealizable_face_states_match_numpy_including_nan(twin, flux, prim):
+    """Face states a limited reconstruction can overshoot into -- negative pressure or density on one side or both -- as the
+    kernel evaluates them (fast pass, plain-operator pass where that declines): the NaN of the square roots must come out where
+    numpy's does (np.maximum.reduce / np.minimum.reduce of flux/HLLL.py:36-37 carry it), because that NaN is what stops the
+    reference's run (Euler2D.py:144-152)."""
+    WL, WR = face_states(12000, seed=57 + FLUX_ID[flux])
+    rng = np.random.default_rng(58)
+    n = len(WL)
+    for Wp, lo in ((WL, 0), (WR, 1)):
+        sel = rng.integers(0, 6, n)
+        Wp[sel == lo, 3] *= -1.0                 # negative pressure on this side
+        Wp[sel == 2 + lo, 0] *= -1.0             # negative density on this side
+        Wp[sel == 4, 3] *= -rng.uniform(0.0, 1e-3, (sel == 4).sum())   # slightly negative pressure on both sides
+    if prim:
+        QL, QR = WL, WR
+    else:
+        with np.errstate(all="ignore"):
+            QL, QR = mo.prim_to_cons(WL, G), mo.prim_to_cons(WR, G)
+            WL, WR = mo.cons_to_prim(QL, G), mo.cons_to_prim(QR, G)
+    with np.errstate(all="ignore"):
+        ref = mo.FLUXES[flux](WL, WR, G)
+    Ff, okf, scale = twin.riemann(FLUX_ID[flux], prim, 1, QL, QR)
+    Fs, _, _ = twin.riemann(FLUX_ID[flux], prim, 0, QL, QR)
+    F = np.where(okf[:, None].astype(bool), Ff, Fs)
+    with np.errstate(all="ignore"):
+        want = scale * ref
+    good = (F == want) | (np.isnan(F) & np.isnan(want))
+    bad = np.nonzero(~np.all(good, axis=1))[0]
+    assert np.isnan(want).any(axis=1).mean() > 0.3
+    assert len(bad) == 0, (flux, prim, len(bad), QL[bad[:2]], QR[bad[:2]], F[bad[:2]], want[bad[:2]])

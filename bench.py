@@ -279,6 +279,7 @@ def run_named(torch, name, device, steps, peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    path, tuning = eng.stage_path(), eng.stage_path_tuning()   # chosen by measurement at the first run() (pyh_stage_path)
     # 3) end to end: host state in (pinned) -> H2D -> ghost refresh -> K steps -> D2H into pinned host buffers
     outs = {g: eng.pinned_state_buffer() for g in gids}
     t0 = time.perf_counter()
@@ -297,7 +298,8 @@ def run_named(torch, name, device, steps, peak):
     return {
         "workload": NAMED[name]["title"], "cells_total": cells, "stages_per_step": nstages, "steps": int(k),
         "value": value, "unit": "cell-stage updates/s", "ms_per_step": ms / max(k, 1), "gpu_launches": int(launches),
-        "stage_kernel_shape": {"lanes": shape[0], "rows_per_strip": shape[1]},
+        "stage_path": path, "stage_path_tuning_ms": {"fused": tuning[0], "split": tuning[1], "what": "ms per stage launch measured at the first pyh_run; the faster path runs"},
+        "stage_kernel_shape": {"lanes": shape[0], "rows_per_strip": shape[1]} if path == "fused" else {"kernels": "k_split_recon (32 x 8 cells per thread block) -> k_split_flux (one thread per face) -> k_split_update (one thread per cell)"},
         "parity": {"bit_identical_to_reference": bool(parity_ok), "checkpoints": meta["checkpoints"],
                    "what": "every dt and the sha256-by-value of every block state at each checkpoint vs the unmodified reference's fingerprint (" + meta["generator"] + ")"},
         "e2e": {"value": cells * nstages * k / e2e_s, "unit": "cell-stage updates/s", "h2d_bytes_per_step": cells * 32 / max(k, 1),
@@ -343,6 +345,7 @@ def run_ours(args):
                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": r["workload"], "cells_total": r["cells_total"], "stages_per_step": r["stages_per_step"], "parity": r["parity"],
                           "l2_policy": "state (%.1f MB) fits the 126 MB L2: this is the reference's own size" % (r["cells_total"] * 32 / 1e6)},
+               "stage_path": r["stage_path"], "stage_kernel_shape": r["stage_kernel_shape"],
                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": dict(r["roofline"], peak_source=peak_src)}
         print(json.dumps(out), flush=True)
         return

@@ -209,6 +209,12 @@ int pyh_debug_fetch(void* ctx, int gid, int what, double* aos_out);
 
 /* Strip shape the stage kernel runs with: lanes per thread block (lanes - 4 output columns) x rows per strip. */
 int pyh_march_shape(void* ctx, int32_t* lanes, int32_t* rows);
+/* Which kernels run a stage: 0 = the fused row-marching kernel (above), 1 = the three per-cell / per-face kernels
+   (pyh_stage_split.cuh) that an eligible context -- one quadrature point, no neighbours on other ranks, at most a few million
+   cells -- uses when they are faster on its blocks.  Decided by measurement at the first pyh_run (tuned_ms: milliseconds per
+   stage launch it saw, {fused, split}; zeros if nothing was measured); the environment variable PYH_SPLIT=0/1, read by
+   pyh_finalize, forces a path.  Same reference calls, same arithmetic, same bits either way.  tuned_ms may be NULL. */
+int pyh_stage_path(void* ctx, int32_t* split, double* tuned_ms);
 /* Counters for bench.py: kernels launched by this context since creation. */
 int pyh_launch_count(void* ctx, int64_t* n);
 /* The CUDA stream all of the context's kernels are launched on (as a cudaStream_t value). */

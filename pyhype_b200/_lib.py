@@ -101,6 +101,7 @@ SIGNATURES = {
     "pyh_residual": (C.c_int, [_vp, C.c_int, c_double_p]),
     "pyh_debug_fetch": (C.c_int, [_vp, C.c_int, C.c_int, c_double_p]),
     "pyh_march_shape": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pyh_stage_path": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "pyh_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "pyh_stream": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pyh_sync": (C.c_int, [_vp]),

@@ -46,6 +46,11 @@ namespace pyh {
 MarchFn pick_march_nq1(int f, int l, int p);
 MarchFn pick_march_nq2(int f, int l, int p);
 MarchFn pick_march_nq3(int f, int l, int p);
+// pyh_split.cu: the three-kernel stage of small problems (pyh_stage_split.cuh)
+SplitReconFn pick_split_recon(int l, int p);
+SplitFluxFn pick_split_flux(int f, int p);
+void launch_split_update(dim3 grid, cudaStream_t st, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+                         const Control* ctl, Control* ctl_out, const Consts C);
 }
 
 namespace {
@@ -84,6 +89,10 @@ struct Ctx {
     double* d_tmp = nullptr;       // small device scratch (dt etc.)
     int march_nt = 128, march_tys = 64;
     bool march_configured = false;   // cudaFuncSetAttribute done for this context's device
+    bool use_split = false;          // every stage as recon / flux / update kernels (pyh_stage_split.cuh) instead of the fused one
+    bool split_ready = false;        // scratch planes of the split path allocated (eligible context)
+    bool path_tuned = false;         // tune_stage_path has run (first pyh_run)
+    double tune_ms[2] = {0.0, 0.0};  // what it measured: ms per stage launch, fused / split
     bool push_ok = false;            // ghost cells are written by the stage kernel itself (plan.push_ghost): no k_ghost / k_pack_halo per stage
     // asynchronous state streaming (pyh_upload_state_async & co)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -252,6 +261,73 @@ int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg) {
     return launch_stage(c, plan, want_grad_dbg, tl[0], c->stream);
 }
 
+// Small and medium problems may take the three-kernel stage (pyh_stage_split.cuh) instead of the fused kernel: one quadrature
+// point, no neighbours on other ranks (their strip exchange is built around the fused kernel's edge / interior launches), and
+// few enough cells that the scratch planes are affordable.  Which of the two is faster depends on how well the block shape
+// fits the fused kernel's strips (measured, profiles/r02o_split_stage_ab.txt: DMR's 4 x 500^2 blocks run 24 % faster split,
+// 8 x 256^2 .. 8 x 1024^2 12-20 % faster fused, explosion_multi's 8 x 150^2 the same), so eligible contexts MEASURE it once, on
+// their own state, at the first pyh_run (tune_stage_path); the results are bit-identical either way.  PYH_SPLIT=0 / 1 forces a
+// path (A/B runs; the GPU tests run every case once per path).
+bool split_eligible(Ctx* c) {
+    if (c->cfg.num_quadrature_points != 1 || c->blocks.empty() || !c->slots.empty()) return false;
+    if (const char* e = getenv("PYH_SPLIT")) return atoi(e) != 0;
+    const long long cells = (long long)c->lay.nx * c->lay.ny * (long long)c->blocks.size();
+    return cells <= kSplitMaxCells;
+}
+
+int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
+    if (c->blocks.empty()) return 0;
+    const int nx = c->lay.nx, ny = c->lay.ny;
+    const unsigned nb = (unsigned)c->blocks.size();
+    SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon);
+    SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon);
+    k1<<<dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), kSplitReconThreads, 0, st>>>(c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C);
+    CU(cudaGetLastError());
+    const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
+    k2<<<dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), kSplitFluxThreads, 0, st>>>(c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C);
+    CU(cudaGetLastError());
+    launch_split_update(dim3(cdiv((long long)nx * ny, kSplitUpdateThreads), 1, nb), st, c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C);
+    CU(cudaGetLastError());
+    c->launches += 3;
+    return 0;
+}
+
+StagePlan make_plan(Ctx* c, int s, int cur, int next);
+int launch_stage(Ctx* c, const StagePlan& plan, int want_grad_dbg);
+
+// Times stage 0 of a step both ways on the context's current state and keeps the faster path.  Stage 0 reads the solution
+// buffer and writes only buffers every step rewrites before reading them (the next stage state, the partial sums), without
+// the CFL reduction or the ghost push, so the solution, the control block and the results are untouched.
+int tune_stage_path(Ctx* c) {
+    if (c->path_tuned) return 0;
+    c->path_tuned = true;
+    if (!c->split_ready || getenv("PYH_SPLIT")) return 0;   // not eligible, or forced
+    const int S = c->cfg.num_stages;
+    StagePlan p = make_plan(c, 0, c->i0, plan_next_buffer(S, 0, c->i0, c->i0, c->i1, c->i2));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float ms[2] = {0.f, 0.f};
+    const long long l0 = c->launches;
+    for (int path = 0; path < 2; ++path) {
+        int rc = 0;
+        for (int rep = 0; rep < 7 && !rc; ++rep) {   // 2 warm-up launches, 5 timed
+            if (rep == 2) CU(cudaEventRecord(e0, c->stream));
+            rc = path ? launch_stage_split(c, p, c->stream) : launch_stage(c, p, 0);
+        }
+        if (rc) return rc;
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms[path], e0, e1));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->launches = l0;                                   // tuning launches are not part of any step
+    c->tune_ms[0] = ms[0] / 5.0; c->tune_ms[1] = ms[1] / 5.0;
+    c->use_split = ms[1] < 0.97f * ms[0];               // ties go to the fused kernel
+    return 0;
+}
+
 // RK partial-sum plan for stage s (explicit_runge_kutta.py:63-75 restated as running sums:
 // row s' accumulates U0 + sum_{k<=s} (dt*a[s'][k]) R_k in k order, exactly the reference's order)
 StagePlan make_plan(Ctx* c, int s, int cur, int next) {
@@ -286,7 +362,7 @@ StagePlan advance_roles(Ctx* c, int s, bool fuse_dt = false) {
 
 int do_stage(Ctx* c, int s) {
     StagePlan p = advance_roles(c, s);
-    return launch_stage(c, p, 0);
+    return c->use_split ? launch_stage_split(c, p, c->stream) : launch_stage(c, p, 0);
 }
 
 int set_active(Ctx* c, int active) {
@@ -347,7 +423,7 @@ int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
         c->split_ns = true;
     }
     if (!force_split && (!c->comm.comm || c->slots.empty() || no_overlap || !c->s_edge)) {
-        if ((rc = launch_stage(c, p, 0))) return rc;
+        if ((rc = c->use_split ? launch_stage_split(c, p, c->stream) : launch_stage(c, p, 0))) return rc;
         if ((rc = exchange_halo(c, c->cur, nullptr, c->push_ok))) return rc;
         return c->push_ok ? 0 : do_ghost(c, c->cur);
     }
@@ -578,6 +654,11 @@ int pyh_finalize(void* ctx) {
         c->comm.doubles = c->halo_doubles;
         for (const HaloSlot& hs : c->slots) c->blocks[hs.blk].dev.send[hs.side] = c->comm.d_send + hs.offset;
     }
+    c->split_ready = split_eligible(c);
+    c->use_split = c->split_ready && getenv("PYH_SPLIT") != nullptr;   // forced; otherwise decided by measurement at the first pyh_run
+    if (c->split_ready)   // limited face states + face fluxes between the three kernels of a stage (L2-resident at the sizes that take this path)
+        for (auto& hb : c->blocks)
+            if (int rc = dalloc(hb, &hb.dev.aux, (long long)kSplitPlanes * c->lay.plane, true)) return rc;
     std::vector<BlkDev> tmp;
     for (auto& hb : c->blocks) tmp.push_back(hb.dev);
     CU(cudaMalloc(&c->d_blks, std::max<size_t>(tmp.size(), 1) * sizeof(BlkDev)));
@@ -944,6 +1025,7 @@ int pyh_run(void* ctx, double* t_inout, double t_final, int64_t max_steps, int32
     h.dts = ddts; h.dts_cap = ddts ? dts_cap : 0;
     CU(cudaMemcpyAsync(c->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     int rc;
+    if ((rc = tune_stage_path(c))) return rc;   // first call only: fused kernel or the three-kernel stage, whichever is faster here
     // one time step: [all-reduce of] the CFL minimum, dt, stages + ghost refresh, t += dt; every kernel early-exits once
     // t >= t_final.  The CFL minimum and the realizability flag of a step's FINAL state are reduced inside its last stage
     // (plan.fuse_dt: the state is still in registers there), so only the first step of a call needs the k_dt pass below.
@@ -1198,6 +1280,14 @@ int pyh_march_shape(void* ctx, int32_t* lanes, int32_t* rows) {
     if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
     if (lanes) *lanes = c->march_nt;
     if (rows) *rows = c->march_tys;
+    return 0;
+}
+
+int pyh_stage_path(void* ctx, int32_t* split, double* tuned_ms) {
+    Ctx* c = as_ctx(ctx);
+    if (!c || !c->finalized) return set_err(PYH_ERR_STATE, "context not finalized");
+    if (split) *split = c->use_split ? 1 : 0;
+    if (tuned_ms) { tuned_ms[0] = c->tune_ms[0]; tuned_ms[1] = c->tune_ms[1]; }
     return 0;
 }
 

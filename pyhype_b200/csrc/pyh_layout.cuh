@@ -86,6 +86,7 @@ struct BlkDev {
     double* base;                 // the block's slab
     double* dbg;                  // 4 planes: residual test hook (allocated on demand)
     double* dbgG;                 // 12 planes: gx[4], gy[4], phi[4] (allocated on demand)
+    double* aux;                  // 24 planes: limited face states + face fluxes of the three-kernel stage of small problems (pyh_stage_split.cuh), else null
     const double* dir_recon[4];   // Dirichlet strips in reconstruction variables (edge_len x 4, AoS)
     const double* dir_cons[4];    // Dirichlet strips in conservative variables
     int bc[4];

@@ -288,6 +288,18 @@ class Engine:
         check(self.lib.pyh_march_shape(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def stage_path(self):
+        """'fused' (row-marching stage kernel) or 'split' (recon / flux / update kernels of small problems)"""
+        a = C.c_int32()
+        check(self.lib.pyh_stage_path(self._ctx, C.byref(a), None))
+        return "split" if a.value else "fused"
+
+    def stage_path_tuning(self):
+        """ms per stage launch the first run() measured for (fused, split); (0, 0) when the path was not chosen by measurement"""
+        a, ms = C.c_int32(), (C.c_double * 2)()
+        check(self.lib.pyh_stage_path(self._ctx, C.byref(a), ms))
+        return ms[0], ms[1]
+
     def launch_count(self):
         n = C.c_int64()
         check(self.lib.pyh_launch_count(self._ctx, C.byref(n)))

@@ -13,6 +13,7 @@
 #include "pyh_kernels.cuh"
 #include "pyh_plan.cuh"
 #include "pyh_stage_march.cuh"
+#include "pyh_stage_split.cuh"
 
 namespace pyh {
 double smem[(24 + 24 * 3) * 256];   // what `extern __shared__ double smem[]` of the kernel resolves to
@@ -47,7 +48,30 @@ static MarchFn pick(int f, int l, int p, int nq) {
     return nullptr;
 }
 
+// the three-kernel stage of small problems (pyh_stage_split.cuh), same set of instantiations
+static SplitReconFn pick_recon(int l, int p) {
+    if (l == 0) return p ? k_split_recon<0, 1> : k_split_recon<0, 0>;
+    if (p) return nullptr;
+    if (l == 1) return k_split_recon<1, 0>;
+    if (l == 2) return k_split_recon<2, 0>;
+    return k_split_recon<3, 0>;
+}
+static SplitFluxFn pick_flux(int f, int p) {
+    switch (2 * f + p) {
+        case 0: return k_split_flux<0, 0>;
+        case 1: return k_split_flux<0, 1>;
+        case 2: return k_split_flux<1, 0>;
+        case 3: return k_split_flux<1, 1>;
+        case 4: return k_split_flux<2, 0>;
+        default: return k_split_flux<2, 1>;
+    }
+}
+
+static long long g_split_stages = 0;   // stages that went through the three-kernel path (tests assert the path was really taken)
+
 extern "C" {
+
+long long twin_split_stages() { return g_split_stages; }
 
 int twin_kernel_fold_pow2() { return PYH_FOLD_POW2; }
 
@@ -63,9 +87,12 @@ struct Twin {
     Control ctl;
     int nx, ny, nblk, nq, nt, tys, prim, mlen;
     size_t nc;
-    std::vector<std::vector<double>> slabs, dbg, dbgG, dirr, dirc;
+    std::vector<std::vector<double>> slabs, dbg, dbgG, dirr, dirc, aux;
     std::vector<BlkDev> blks;
     MarchFn fn;
+    SplitReconFn fn_recon = nullptr;
+    SplitFluxFn fn_flux = nullptr;
+    bool splitpath = false;
 
     int setup(int flux, int lim, int prim_, int nq_, int nx_, int ny_, int nblk_, int nt_, int tys_, double gamma, int S, const double* tab,
               const double* nodes_x, const double* nodes_y, const double* area, const double* cos_v, const double* sin_v,
@@ -75,6 +102,12 @@ struct Twin {
         if (nt < 6 || nt > 256 || nq < 1 || nq > 3 || tys < 1 || S < 1 || S > PYH_MAX_STAGES) return -1;
         fn = pick(flux, lim, prim, nq);
         if (!fn) return -2;   // instantiation not compiled into the twin
+        if (const char* e = getenv("PYH_TWIN_SPLITPATH")) splitpath = atoi(e) != 0 && nq == 1;   // pyh_api.cu: choose_split
+        if (splitpath) {
+            fn_recon = pick_recon(lim, prim);
+            fn_flux = pick_flux(flux, prim);
+            if (!fn_recon || !fn_flux) return -2;
+        }
         lay.nx = nx; lay.ny = ny;
         lay.pitch = ((nx + PADL + 1 + 3) / 4) * 4;                     // pyh_create
         lay.plane = (unsigned)((ny + 2) * lay.pitch);
@@ -89,6 +122,7 @@ struct Twin {
         const size_t nn = (size_t)(ny + 1) * (nx + 1), nv = (size_t)ny * (nx + 1), nh = (size_t)(ny + 1) * nx;
         nc = (size_t)ny * nx;
         mlen = std::max(nx, ny);
+        aux.assign(nblk, {});
         slabs.assign(nblk, {}); dbg.assign(nblk, {}); dbgG.assign(nblk, {}); dirr.assign(nblk * 4, {}); dirc.assign(nblk * 4, {});
         blks.assign(nblk, BlkDev());
         std::memset(&ctl, 0, sizeof(ctl));
@@ -115,6 +149,7 @@ struct Twin {
             D.base = slab;
             D.dbg = dbg[b].data();
             D.dbgG = dbgG[b].data();
+            if (splitpath) { aux[b].assign((size_t)kSplitPlanes * lay.plane, 0.0); D.aux = aux[b].data(); }
             for (int s = 0; s < 4; ++s) {
                 D.bc[s] = bc[4 * b + s];
                 D.nbr[s] = nbr[4 * b + s];
@@ -146,6 +181,17 @@ struct Twin {
     }
     void stage(const StagePlan& plan, int want_grad_dbg) {   // launch_stage: the product's tile plan (PYH_TWIN_SPLIT = 1: north /
         // south edge strips apart, 2: east / west edge columns apart, 3: both -- what a context with remote neighbours launches)
+        if (splitpath && !want_grad_dbg && !plan.write_residual) {   // launch_stage_split: recon -> flux -> update
+            launch(dim3(cdivu(nx, kSplitTX), cdivu(ny, kSplitTY), nblk), kSplitReconThreads, true,
+                   [&] { fn_recon(blks.data(), lay, po, plan.cur, &ctl, C); });
+            const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
+            launch(dim3(cdivu(nfaces, kSplitFluxThreads), 2, nblk), kSplitFluxThreads, false,
+                   [&] { fn_flux(blks.data(), lay, po, plan.cur, &ctl, C); });
+            launch(dim3(cdivu((long long)nx * ny, kSplitUpdateThreads), 1, nblk), kSplitUpdateThreads, true,
+                   [&] { k_split_update(blks.data(), lay, po, plan, &ctl, &ctl, C); });
+            ++g_split_stages;
+            return;
+        }
         const char* e = getenv("PYH_TWIN_SPLIT");
         const int split = e ? atoi(e) : 0;
         TileLaunch tl[3];

@@ -14,7 +14,7 @@ import pytest
 
 import cases
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("stage_path")]   # every test once per stage implementation (conftest.py)
 
 KW = dict(integrator="ExplicitEuler1", CFL=0.3)
 

@@ -13,7 +13,7 @@ from pyhype_b200.solver_config import SolverConfig
 from pyhype_b200.solvers import Euler2D
 from pyhype_b200.states import ConservativeState, PrimitiveState
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("stage_path")]   # every test once per stage implementation (conftest.py)
 
 
 class ExplosionInitialCondition(InitialCondition):

@@ -7,7 +7,7 @@ import pytest
 import cases
 import golden_io
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("stage_path")]   # every test once per stage implementation (conftest.py)
 
 DEVICE_FIXTURES = golden_io.names()
 
@@ -17,11 +17,12 @@ def rel_linf(a, b):
 
 
 @pytest.mark.parametrize("name", DEVICE_FIXTURES)
-def test_engine_matches_reference_fixture(name):
+def test_engine_matches_reference_fixture(name, stage_path):
     fx = golden_io.Fixture(name)
     states = {g: fx[f"U0_{g}"] for g in fx.gids}
     eng = cases.build_engine(fx.blocks, fx.nx, fx.ny, None, states=states, **fx.scheme())
     try:
+        assert eng.stage_path() == (stage_path if fx.scheme()["nqp"] == 1 else "fused")
         for g in fx.gids:
             m = eng.meshes[g]
             assert np.array_equal(m.area, fx[f"A_{g}"]) and np.array_equal(m.x[:, :, 0], fx[f"xc_{g}"])

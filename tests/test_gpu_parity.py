@@ -7,7 +7,7 @@ import pytest
 
 import cases
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("stage_path")]   # every test once per stage implementation (conftest.py)
 
 
 def rel_linf(a, b):

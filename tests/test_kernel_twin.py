@@ -350,3 +350,55 @@ def test_tile_plan_covers_every_cell_once_and_edges_precede_the_exchange(lib_def
         assert edge[:, 0].all() and edge[:, -1].all()
     if not ns and not ew:
         assert n == 1 and edge.all()       # single rank: one launch, nothing to overlap
+
+
+# ---- the three-kernel stage of small problems (pyh_stage_split.cuh) ------------------------------------------------------------
+SPLIT_STEPS = ["em_roe_venkat_cons_rk4", "dmr_hlll_venkat_prim_rk2", "wedge_roe_cons_rk2", "jet_hlle_prim_rk2", "step_hlll_prim_rk2",
+               "em_int_DormandPrince5", "em_int_ExplicitEuler1", "em_lim_VanLeer", "em_lim_VanAlbada", "em_lim_BarthJespersen",
+               "em_ragged_roe_rk4", "cart_roe_cons_rk4"]
+
+
+@pytest.fixture
+def split_path(monkeypatch, lib_default):
+    monkeypatch.setenv("PYH_TWIN_SPLITPATH", "1")
+    lib_default.twin_split_stages.restype = C.c_longlong
+    return lib_default
+
+
+@pytest.mark.parametrize("name", [n for n in SPLIT_STEPS if n in golden_io.names()])
+def test_split_stage_kernels_whole_time_steps_match_reference_fixture(split_path, name):
+    """k_split_recon -> k_split_flux -> k_split_update (what contexts of small problems launch per stage instead of the fused
+    kernel) through the product's plan logic, ghost push included: the state after N steps is the reference's, bit for bit --
+    every flux, both reconstruction modes, the four limiters, Dirichlet / reflection / outflow edges, skewed and Cartesian
+    blocks, a single-stage and a seven-stage tableau."""
+    fx = golden_io.Fixture(name)
+    before = split_path.twin_split_stages()
+    idx, Uout = run_steps(split_path, fx, nt=32, tys=64)
+    assert split_path.twin_split_stages() > before
+    for g in fx.gids:
+        assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g, np.abs(Uout[idx[g]] - fx[f"U_{g}"]).max())
+
+
+@pytest.mark.parametrize("name", ["em_roe_venkat_cons_rk4", "dmr_hlll_venkat_prim_rk2", "em_int_ExplicitEuler1"])
+def test_split_stage_kernels_in_the_device_resident_time_loop(split_path, name):
+    """... and inside pyh_run's loop: the CFL minimum k_split_update reduces for the next step (warp shuffles + atomicMin) gives the
+    reference's dt sequence."""
+    fx = golden_io.Fixture(name)
+    n = fx.meta["steps"]
+    before = split_path.twin_split_stages()
+    idx, Uout, dts, t, nsteps, bad = run_loop(split_path, fx, 0.0, 1e9, n)
+    assert split_path.twin_split_stages() > before
+    assert nsteps == n and not bad
+    assert list(dts) == list(fx["dts"])
+    for g in fx.gids:
+        assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g)
+
+
+def test_split_stage_kernels_flag_unrealizable_states_and_nan(split_path):
+    import test_named_configs as N
+
+    fp = N.Named("shockbox")            # the reference's own abort: NaN through the limiter in step 24
+    n = fp.meta["aborts_in_step"]
+    idx, Uout, dts, t, nsteps, bad = run_loop(split_path, fp, 0.0, fp.meta["t_final_nd"], n + 2, nt=64, tys=16)
+    assert bad and nsteps == n and np.array_equal(dts[: n - 1], fp.dts[: n - 1])
+    assert np.isnan(Uout[idx[fp.gids[0]]]).sum() == 16

@@ -87,10 +87,11 @@ ALL_NAMED = ["em", "dmr", "wedge", "wedge_roe", "jet", "jet_hlle", "ws1024", "ws
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ALL_NAMED)
-def test_named_config_at_named_size_reproduces_the_reference(name):
+def test_named_config_at_named_size_reproduces_the_reference(name, stage_path):
     fp = Named(name)
     eng = cases.build_engine(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
     try:
+        assert eng.stage_path() == stage_path
         done_total, t = 0, 0.0
         for n in fp.meta["checkpoints"]:
             k = n - done_total

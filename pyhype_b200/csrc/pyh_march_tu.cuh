@@ -26,13 +26,13 @@ struct MarchTiles {
 struct BlkDev;
 struct Control;
 typedef void (*MarchFn)(const BlkDev*, const Layout, const PlaneOffsets, const StagePlan, const Control*, Control*, const Consts, const int, const int, const MarchTiles);
-// the three-kernel stage of small problems (pyh_stage_split.cuh)
+// the three-kernel stage (pyh_stage_split.cuh)
 typedef void (*SplitReconFn)(const BlkDev*, const Layout, const PlaneOffsets, const unsigned, const Control*, const Consts);
 typedef void (*SplitFluxFn)(const BlkDev*, const Layout, const PlaneOffsets, const unsigned, const Control*, const Consts);
 constexpr int kSplitTX = 32, kSplitTY = 8;                 // cell tile of k_split_recon (one thread per cell)
 constexpr int kSplitReconThreads = kSplitTX * kSplitTY;
 constexpr int kSplitFluxThreads = 128;
-constexpr int kSplitUpdateThreads = 128;
+constexpr int kSplitUpdateThreads = 256;
 constexpr int kSplitPlanes = 24;                            // FS: 16 (E, W, N, S x 4 variables), FX: 8 (vertical, horizontal faces x 4)
 constexpr long long kSplitMaxCells = 4500000;               // above: always the fused kernel (the scratch planes cost 192 B per cell; 8 x 1024^2 was 20 % slower split)
 // shared-memory doubles per thread for NQ quadrature points per face:

@@ -1,4 +1,4 @@
-// pyh_stage_split.cuh -- the RK stage of SMALL problems as three kernels (sm_100a, fp64), one thread per cell / per face.
+// pyh_stage_split.cuh -- the RK stage as THREE kernels (sm_100a, fp64), one thread per cell / face: for problems the fused kernel's strips fit badly.
 //
 // Same reference path and the same arithmetic, operation for operation, as the fused row-marching kernel of
 // pyh_stage_march.cuh (fvm/base.py:108-500, fvm/SecondOrderMUSCL.py, limiters/base.py, gradients/greengauss.py,
@@ -8,16 +8,20 @@
 // rows of gradient + limiter and one extra face solve at its boundaries, and a thread block lives for (rows + 1) row times.
 // On the reference's own examples (explosion_multi: 8 x 150^2 = 180 k cells, DMR: 4 x 500^2) that means strips of 3-16
 // rows, +43 % redundant work and a third of the GPU's warp slots in use (profiles/r02k_em_stage_march_ncu_summary.txt).
-// At these sizes the face states and fluxes (192 B per cell) stay in the 126 MB L2, so passing them between kernels through
-// global memory costs no DRAM traffic, removes every redundant row, and exposes one thread per cell / face:
+// Here the limited face states and the face fluxes (192 B per cell) pass between three kernels through global memory --
+// L2-resident at the sizes this path is meant for --, which removes every redundant row and exposes one thread per cell / face:
 //
 //     k_split_recon  : cell (i, j)  -> gradient, limiter, the four limited face states        -> FS[face][var]   (16 planes)
 //     k_split_flux   : face         -> ghost-side state / BC, rotation, Riemann solve, x L   -> FX[dir][var]    (8 planes)
 //     k_split_update : cell (i, j)  -> residual, RK partial sums, CFL minimum, ghost push    -> state buffers
 //
-// For problems of more than a few waves the fused kernel wins (no 440 B/cell-stage of extra traffic once the scratch no
-// longer fits the L2); pyh_api.cu picks by size (`choose_split`), PYH_SPLIT=0/1 overrides.  One quadrature point only
-// (every shipped example); 2 / 3 points always take the fused kernel.
+// (Measured alternative: flux + update in ONE kernel, 32 x 8 thread tiles that hold all four faces of 31 x 7 cells, fluxes in
+// shared memory.  explosion_multi 0.161 instead of 0.177 ms/step, but DMR's HLLL solves -- 122 registers, two per thread in
+// sequence, +18 % of them redundant -- 0.514 instead of 0.434: profiles/r02p_split_stage_merged_ab.txt.  Not kept.)
+//
+// Whether this or the fused kernel is faster depends on how the block shape fits the fused kernel's strips, so eligible
+// contexts measure both at the first pyh_run (pyh_api.cu: tune_stage_path); PYH_SPLIT=0/1 forces a path.  One quadrature
+// point only (every shipped example); 2 / 3 points always take the fused kernel.
 #pragma once
 #include "pyh_layout.cuh"
 #include "pyh_math.cuh"
@@ -42,6 +46,8 @@ __device__ __forceinline__ void split_to_recon(double q[4], const Consts& C) {
 }
 
 // ---- 1: gradient + limiter + limited face states ------------------------------------------------------------------------
+// (Requesting the cell's 21 geometry values BEFORE the tile of states is staged, so that their latency overlaps the staging and
+// the barrier, was measured and lost: explosion_multi 0.1726 vs 0.1676 ms/step, profiles/r02p_split_stage_merged_ab.txt.)
 template <int LIM, int PRIM>
 __global__ void __launch_bounds__(kSplitReconThreads, 3)
 k_split_recon(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
@@ -57,40 +63,47 @@ k_split_recon(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
     const unsigned PL = lay.plane;
     const int t = threadIdx.x;
     const int j0 = (int)blockIdx.x * TX, i0 = (int)blockIdx.y * TY;
+    const int tx = t % TX, ty = t / TX;
+    const int i = i0 + ty, j = j0 + tx;
+    const bool mine = (i < ny) && (j < nx);
+    const unsigned o = lay.at(mine ? i : 0, mine ? j : 0);
+    const unsigned oE = o + 1, oN = o + pitch;
+    double gL[4], gc[4], gs[4], Acell, dx[4], dy[4];
+    auto load_geometry = [&]() {
+        gL[0] = PYH_RO(G[po.Lv + oE]); gL[1] = PYH_RO(G[po.Lv + o]); gL[2] = PYH_RO(G[po.Lh + oN]); gL[3] = PYH_RO(G[po.Lh + o]);
+        gc[0] = PYH_RO(G[po.cv + oE]); gc[1] = PYH_RO(G[po.cv + o]); gc[2] = PYH_RO(G[po.ch + oN]); gc[3] = PYH_RO(G[po.ch + o]);
+        gs[0] = PYH_RO(G[po.sv + oE]); gs[1] = PYH_RO(G[po.sv + o]); gs[2] = PYH_RO(G[po.sh + oN]); gs[3] = PYH_RO(G[po.sh + o]);
+        Acell = PYH_RO(G[po.A + o]);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            dx[f] = PYH_RO(G[po.dxy + (f * 2) * PL + o]);
+            dy[f] = PYH_RO(G[po.dxy + (f * 2 + 1) * PL + o]);
+        }
+    };
     for (int e = t; e < SX * SY; e += kSplitReconThreads) {
         const int li = e / SX, lj = e - li * SX;
-        const int i = i0 - 1 + li, j = j0 - 1 + lj;
+        const int ci = i0 - 1 + li, cj = j0 - 1 + lj;
         double q[4] = {1.0, 0.0, 0.0, 1.0};
-        if (split_cell_exists(lay, i, j)) {
-            const unsigned o = lay.at(i, j);
-            q[0] = PYH_RO(U[o]); q[1] = PYH_RO(U[o + PL]); q[2] = PYH_RO(U[o + 2 * PL]); q[3] = PYH_RO(U[o + 3 * PL]);
+        if (split_cell_exists(lay, ci, cj)) {
+            const unsigned oc = lay.at(ci, cj);
+            q[0] = PYH_RO(U[oc]); q[1] = PYH_RO(U[oc + PL]); q[2] = PYH_RO(U[oc + 2 * PL]); q[3] = PYH_RO(U[oc + 3 * PL]);
             split_to_recon<PRIM>(q, C);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) sq[k][li][lj] = q[k];
     }
     __syncthreads();
-    const int tx = t % TX, ty = t / TX;
-    const int i = i0 + ty, j = j0 + tx;
-    if (i >= ny || j >= nx) return;
-    const unsigned o = lay.at(i, j);
-    const unsigned oE = o + 1, oN = o + pitch;
+    if (!mine) return;
+    load_geometry();
     // GreenGauss._get_gradinet_JIT (gradients/greengauss.py:110-155); same expressions as phase B of k_stage_march
-    double LE = PYH_RO(G[po.Lv + oE]), LW = PYH_RO(G[po.Lv + o]), LN = PYH_RO(G[po.Lh + oN]), LS = PYH_RO(G[po.Lh + o]);
+    double LE = gL[0], LW = gL[1], LN = gL[2], LS = gL[3];
 #if PYH_FOLD_POW2
     LE = 0.5 * LE; LW = 0.5 * LW; LN = 0.5 * LN; LS = 0.5 * LS;
 #endif
-    const double xlE = LE * PYH_RO(G[po.cv + oE]), xlW = LW * (-PYH_RO(G[po.cv + o]));
-    const double xlN = LN * PYH_RO(G[po.ch + oN]), xlS = LS * (-PYH_RO(G[po.ch + o]));
-    const double ylE = LE * PYH_RO(G[po.sv + oE]), ylW = LW * (-PYH_RO(G[po.sv + o]));
-    const double ylN = LN * PYH_RO(G[po.sh + oN]), ylS = LS * (-PYH_RO(G[po.sh + o]));
-    const double Acell = PYH_RO(G[po.A + o]);
-    double dx[4], dy[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        dx[f] = PYH_RO(G[po.dxy + (f * 2) * PL + o]);
-        dy[f] = PYH_RO(G[po.dxy + (f * 2 + 1) * PL + o]);
-    }
+    const double xlE = LE * gc[0], xlW = LW * (-gc[1]);
+    const double xlN = LN * gc[2], xlS = LS * (-gc[3]);
+    const double ylE = LE * gs[0], ylW = LW * (-gs[1]);
+    const double ylN = LN * gs[2], ylS = LS * (-gs[3]);
     bool okA = true;
     double ia = Ar<true>::rcp(Acell, okA);
     if (!okA) ia = 1.0 / Acell;
@@ -126,25 +139,14 @@ k_split_recon(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffs
 }
 
 // ---- 2: one Riemann problem per face ------------------------------------------------------------------------------------
-// blockIdx.y = 0: vertical faces (i, J), i in [0, ny), J in [0, nx] (the west face of cell (i, J));
-// blockIdx.y = 1: horizontal faces (I, j), I in [0, ny], j in [0, nx) (the south face of cell (I, j)).
+// One face of one cell: ghost-side state / boundary condition, rotation into the face frame, Riemann solve, rotation back, x L.
+// horiz == false: the west face of cell (i, j), i in [0, ny), j in [0, nx]; true: the south face of cell (i, j), i in [0, ny], j in [0, nx).
 template <int FLUX, int PRIM>
-__global__ void __launch_bounds__(kSplitFluxThreads)
-k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
-             const Consts C) {
-    if (!ctl->active) return;
-    const BlkDev& B = blks[blockIdx.z];
-    const double* __restrict__ const U = B.base + cur;
-    const double* __restrict__ const G = B.base;
-    const double* __restrict__ const FS = B.aux;
-    double* __restrict__ const FX = B.aux + 16 * (size_t)lay.plane;
+__device__ __forceinline__ void split_face_flux(const BlkDev& B, const double* __restrict__ U, const double* __restrict__ G,
+                                                const double* __restrict__ FS, const Layout& lay, const PlaneOffsets& po, const Consts& C,
+                                                const bool horiz, const int i, const int j, double out[4]) {
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
-    const bool horiz = blockIdx.y != 0;
-    const int W = horiz ? nx : nx + 1;
-    const unsigned n = blockIdx.x * (unsigned)kSplitFluxThreads + threadIdx.x;   // faces of one family per block < 2^31
-    const int i = (int)(n / (unsigned)W), j = (int)(n - (unsigned)i * (unsigned)W);
-    if (i >= (horiz ? ny + 1 : ny)) return;
     const unsigned o = lay.at(i, j);
     const int cart = B.cart & 1;
     const bool vident = cart || (PYH_SKIP_UNIT_ROT && (B.cart & 2));
@@ -208,16 +210,39 @@ k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffse
     else unrot(Fq[1], Fq[2], cf, sf);
     // integrate_flux (fvm/base.py:188-190), one point: L * (0 + 2 F); riemann_flux returns flux_scale(FLUX) * F
     const double Lf1 = (flux_scale(FLUX) == 2.0) ? Lf : 2.0 * Lf;
-    double* __restrict__ const out = FX + (horiz ? 4 : 0) * (size_t)PL + o;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out[k * (size_t)PL] = PYH_FOLD_POW2 ? Lf1 * Fq[k] : Lf * (2.0 * Fq[k]);
+    for (int k = 0; k < 4; ++k) out[k] = PYH_FOLD_POW2 ? Lf1 * Fq[k] : Lf * (2.0 * Fq[k]);
+}
+
+// One thread per face.  blockIdx.y = 0: vertical faces (i, J), i in [0, ny), J in [0, nx] (the west face of cell (i, J));
+// blockIdx.y = 1: horizontal faces (I, j), I in [0, ny], j in [0, nx) (the south face of cell (I, j)).
+template <int FLUX, int PRIM>
+__global__ void __launch_bounds__(kSplitFluxThreads)
+k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
+             const Consts C) {
+    if (!ctl->active) return;
+    const BlkDev& B = blks[blockIdx.z];
+    const int nx = lay.nx, ny = lay.ny;
+    const bool horiz = blockIdx.y != 0;
+    const int W = horiz ? nx : nx + 1;
+    const unsigned n = blockIdx.x * (unsigned)kSplitFluxThreads + threadIdx.x;   // faces of one family per block < 2^31
+    const int i = (int)(n / (unsigned)W), j = (int)(n - (unsigned)i * (unsigned)W);
+    if (i >= (horiz ? ny + 1 : ny)) return;
+    double F[4];
+    split_face_flux<FLUX, PRIM>(B, B.base + cur, B.base, B.aux, lay, po, C, horiz, i, j, F);
+    double* __restrict__ const out = B.aux + (16 + (horiz ? 4 : 0)) * (size_t)lay.plane + lay.at(i, j);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k * (size_t)lay.plane] = F[k];
 }
 
 // ---- 3: residual + RK partial sums (+ CFL minimum of the new state, ghost push) ------------------------------------------
-__global__ void __launch_bounds__(kSplitUpdateThreads)
+// One thread per cell, every load issued before the first use (the kernel is a chain of dependent memory round trips, not
+// arithmetic), all cells of explosion_multi resident at once (5 x 256 threads per SM).
+__global__ void __launch_bounds__(kSplitUpdateThreads, 5)
 k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan, const Control* __restrict__ ctl,
                Control* __restrict__ ctl_out, const Consts C) {
     if (!ctl->active) return;
+    __shared__ double sDT[kSplitUpdateThreads / 32];
     const BlkDev& B = blks[blockIdx.z];
     double* __restrict__ const base = B.base;
     const double* __restrict__ const G = B.base;
@@ -230,15 +255,19 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
     double tm = __longlong_as_double(0x7ff0000000000000ll);
     if (live) {
         const unsigned o = lay.at(i, j);
+        const int nt_ = plan.ntargets;
         const double a = PYH_RO(G[po.A + o]);
-        double IW[4], IE[4], IS[4], IN[4];
+        double dI[4], s0[4], s1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            IW[k] = FX[k * (size_t)PL + o];
-            IE[k] = FX[k * (size_t)PL + o + 1];
-            IS[k] = FX[(4 + k) * (size_t)PL + o];
-            IN[k] = FX[(4 + k) * (size_t)PL + o + pitch];
+            const double IWp = FX[k * (size_t)PL + o], IEp = FX[k * (size_t)PL + o + 1];
+            const double ISp = FX[(4 + k) * (size_t)PL + o], INp = FX[(4 + k) * (size_t)PL + o + pitch];
+            s0[k] = (nt_ > 0) ? base[plan.t[0].src + k * PL + o] : 0.0;
+            s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + o] : 0.0;
+            dI[k] = IWp - IEp + ISp - INp;
         }
+        double cdx = 1.0, cdy = 1.0;
+        if (plan.fuse_dt) { cdx = PYH_RO(G[po.cdx + o]); cdy = PYH_RO(G[po.cdy + o]); }
         // D: residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89), as in k_stage_march
         double Rk[4];
         auto resid = [&](auto tag) -> bool {
@@ -248,53 +277,28 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
 #if PYH_FOLD_POW2
-                Rk[k] = Ar<FAST>::div(IW[k] - IE[k] + IS[k] - IN[k], ra, ok);        // = 2 R; the 0.5 moves into the RK coefficient
+                Rk[k] = Ar<FAST>::div(dI[k], ra, ok);                                  // = 2 R; the 0.5 moves into the RK coefficient
 #else
-                Rk[k] = Ar<FAST>::div(0.5 * (IW[k] - IE[k] + IS[k] - IN[k]), ra, ok);
+                Rk[k] = Ar<FAST>::div(0.5 * dI[k], ra, ok);
 #endif
             }
             return ok;
         };
         if (!resid(FastTag{})) resid(SafeTag{});
         constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
-        const int nt_ = plan.ntargets;
+        double un[4] = {0.0, 0.0, 0.0, 0.0};
         if (nt_ > 0) {
             const double c0 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[0].coef] : ctl->coef[plan.t[0].coef];
-            double un[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double s0 = base[plan.t[0].src + k * PL + o];
-                un[k] = plan.t[0].add ? s0 + c0 * Rk[k] : s0;
+                un[k] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k];
                 base[plan.t[0].dst + k * PL + o] = un[k];
-            }
-            if (plan.fuse_dt) {
-                // QuadBlock.get_dt (quad_block.py:423-436) + realizability (states/conservative.py:161-165) of the state this step ends with
-                const double cdx = PYH_RO(G[po.cdx + o]), cdy = PYH_RO(G[po.cdy + o]);
-                double tx_, ty_;
-                auto cfl = [&](auto tag) -> bool {
-                    constexpr bool FAST = decltype(tag)::value;
-                    bool ok = true;
-                    typename Ar<FAST>::R rr = Ar<FAST>::recip(un[0], ok);
-                    const double u = Ar<FAST>::div(un[1], rr, ok), v = Ar<FAST>::div(un[2], rr, ok);
-                    const double p = C.gm1 * (un[3] - un[0] * (0.5 * (u * u + v * v)));
-                    const double a_ = Ar<FAST>::sqrt(Ar<FAST>::div(C.g * p, rr, ok), ok);
-                    tx_ = Ar<FAST>::div(cdx, fabs(u) + a_, ok);
-                    ty_ = Ar<FAST>::div(cdy, fabs(v) + a_, ok);
-                    return ok;
-                };
-                if (!cfl(FastTag{})) cfl(SafeTag{});
-                tm = dmin2(tx_, ty_);
-                // unrealizable (or NaN): -inf can never be a CFL time, so it doubles as the flag
-                if (!(un[0] > 0.0) || !(un[3] > 0.0) || (tm != tm)) tm = __longlong_as_double(0xfff0000000000000ll);
             }
         }
         if (nt_ > 1) {   // targets 0 and 1 by static index (no local copy of the plan), the rare rest by a loop
             const double c1 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[1].coef] : ctl->coef[plan.t[1].coef];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double src = base[plan.t[1].src + k * PL + o];
-                base[plan.t[1].dst + k * PL + o] = plan.t[1].add ? src + c1 * Rk[k] : src;
-            }
+            for (int k = 0; k < 4; ++k) base[plan.t[1].dst + k * PL + o] = plan.t[1].add ? s1[k] + c1 * Rk[k] : s1[k];
         }
         for (int q = 2; q < nt_; ++q) {   // tableaux with more than two live rows (e.g. DormandPrince5)
             const double cq = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[q].coef] : ctl->coef[plan.t[q].coef];
@@ -304,6 +308,25 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
                 base[plan.t[q].dst + k * PL + o] = plan.t[q].add ? src + cq * Rk[k] : src;
             }
         }
+        if (plan.fuse_dt && nt_ > 0) {
+            // QuadBlock.get_dt (quad_block.py:423-436) + realizability (states/conservative.py:161-165) of the state this step ends with
+            double tx_, ty_;
+            auto cfl = [&](auto tag) -> bool {
+                constexpr bool FAST = decltype(tag)::value;
+                bool ok = true;
+                typename Ar<FAST>::R rr = Ar<FAST>::recip(un[0], ok);
+                const double u = Ar<FAST>::div(un[1], rr, ok), v = Ar<FAST>::div(un[2], rr, ok);
+                const double p = C.gm1 * (un[3] - un[0] * (0.5 * (u * u + v * v)));
+                const double a_ = Ar<FAST>::sqrt(Ar<FAST>::div(C.g * p, rr, ok), ok);
+                tx_ = Ar<FAST>::div(cdx, fabs(u) + a_, ok);
+                ty_ = Ar<FAST>::div(cdy, fabs(v) + a_, ok);
+                return ok;
+            };
+            if (!cfl(FastTag{})) cfl(SafeTag{});
+            tm = dmin2(tx_, ty_);
+            // unrealizable (or NaN): -inf can never be a CFL time, so it doubles as the flag
+            if (!(un[0] > 0.0) || !(un[3] > 0.0) || (tm != tm)) tm = __longlong_as_double(0xfff0000000000000ll);
+        }
         if (plan.push_ghost && nt_ > 0) {
             // ghost cells mirroring an edge cell this thread has just written (target 0 is the stage's output state)
             const unsigned dst = plan.t[0].dst;
@@ -311,12 +334,18 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             if (j == 0 || j == nx - 1) push_ghost_cell(blks, B, lay, po, dst, i, j, false);
         }
     }
-    if (plan.fuse_dt) {   // warp minimum -> one atomicMin per warp (quad_block.py:436: min over cells; Solver.get_dt: over blocks)
+    if (plan.fuse_dt) {   // block minimum -> one atomicMin per thread block (quad_block.py:436: min over cells; Solver.get_dt: over blocks)
+        const int t = threadIdx.x;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) tm = dmin2(tm, __shfl_xor_sync(0xffffffffu, tm, s));
-        if ((threadIdx.x & 31) == 0) {
-            if (tm == __longlong_as_double(0xfff0000000000000ll)) { atomicOr(&ctl_out->bad, 1); atomicExch(&ctl_out->allok, 0ull); }
-            else atomicMin(&ctl_out->dtmin_bits, dkey(tm));
+        if ((t & 31) == 0) sDT[t >> 5] = tm;
+        __syncthreads();
+        if (t == 0) {
+            double m = sDT[0];
+#pragma unroll
+            for (int w = 1; w < kSplitUpdateThreads / 32; ++w) m = dmin2(m, sDT[w]);
+            if (m == __longlong_as_double(0xfff0000000000000ll)) { atomicOr(&ctl_out->bad, 1); atomicExch(&ctl_out->allok, 0ull); }
+            else atomicMin(&ctl_out->dtmin_bits, dkey(m));
         }
     }
 }

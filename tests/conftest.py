@@ -34,7 +34,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(params=["fused", "split"])
 def stage_path(request, monkeypatch):
     """Run a GPU test once per stage implementation: the fused row-marching kernel (pyh_stage_march.cuh) and the three-kernel
-    stage that contexts of small problems use (pyh_stage_split.cuh).  pyh_finalize reads PYH_SPLIT; without it the size rule
-    would send every small fixture through the split path only.  (Two / three quadrature points always run fused.)"""
+    stage (pyh_stage_split.cuh).  pyh_finalize reads PYH_SPLIT; without it a context takes whichever path its first run()
+    measures as faster on its blocks.  (Two / three quadrature points always run fused.)"""
     monkeypatch.setenv("PYH_SPLIT", "1" if request.param == "split" else "0")
     return request.param

@@ -413,7 +413,7 @@ int stage_and_refresh(Ctx* c, int s, bool fuse_dt = false) {
     static const bool no_overlap = getenv("PYH_NO_HALO_OVERLAP") != nullptr;   // diagnostics: blocking exchange behind one launch
     StagePlan p = advance_roles(c, s, fuse_dt);
     int rc;
-    static const bool force_split = getenv("PYH_FORCE_SPLIT") != nullptr;      // diagnostics: the edge / interior split on ONE rank
+    static const bool force_split = getenv("PYH_FORCE_EDGE_SPLIT") != nullptr;      // diagnostics: the edge / interior split on ONE rank
     if (force_split && !c->s_edge && !c->blocks.empty()) {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));

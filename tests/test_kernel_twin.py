@@ -382,7 +382,7 @@ def test_split_stage_kernels_whole_time_steps_match_reference_fixture(split_path
         assert np.array_equal(Uout[idx[g]], fx[f"U_{g}"]), (name, g, np.abs(Uout[idx[g]] - fx[f"U_{g}"]).max())
 
 
-@pytest.mark.parametrize("name", ["em_roe_venkat_cons_rk4", "em_int_ExplicitEuler1"] + (["dmr_hlll_venkat_prim_rk2"] if os.environ.get("PYH_TWIN_ALL") else []))
+@pytest.mark.parametrize("name", ["cart_roe_cons_rk4", "em_int_ExplicitEuler1"] + (["em_roe_venkat_cons_rk4", "dmr_hlll_venkat_prim_rk2"] if os.environ.get("PYH_TWIN_ALL") else []))
 def test_split_stage_kernels_in_the_device_resident_time_loop(split_path, name):
     """... and inside pyh_run's loop: the CFL minimum k_split_update reduces for the next step (warp shuffles + atomicMin) gives the
     reference's dt sequence."""

@@ -130,10 +130,11 @@ def test_oracle_restatement_at_named_size_first_checkpoint(name):
 def test_stage_kernel_source_twin_at_named_size_first_checkpoint(name):
     """The device-resident time loop of the product (k_dt, k_dt_finalize, k_stage_march in the shipped 128-thread x 64-row
     strip shape, k_ghost, k_step_end), compiled by g++ and run by the thread-block emulator of tests/host_twin/, at the named
-    size: two column strips and three row strips per 150 x 150 block, four by eight per 500 x 500 block.  The DMR case
-    takes two minutes of emulation and runs only with PYH_NAMED_TWIN_ALL=1 (last run: profiles/r01u_named_config_parity.md)."""
-    if name == "dmr" and not os.environ.get("PYH_NAMED_TWIN_ALL"):
-        pytest.skip("two minutes of emulation: set PYH_NAMED_TWIN_ALL=1")
+    size: two column strips and three row strips per 150 x 150 block, four by eight per 500 x 500 block.  One and two
+    minutes of emulation: they run only with PYH_NAMED_TWIN_ALL=1 (last run: profiles/r02r_named_twin.txt)."""
+    if not os.environ.get("PYH_NAMED_TWIN_ALL"):
+        pytest.skip("one (explosion_multi) and two (DMR) minutes of emulation: set PYH_NAMED_TWIN_ALL=1; the shockbox replay below is the "
+                    "named-size twin run of the default suite")
     import test_kernel_twin as T
 
     fp = Named(name)

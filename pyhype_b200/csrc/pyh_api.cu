@@ -49,8 +49,12 @@ MarchFn pick_march_nq3(int f, int l, int p);
 // pyh_split.cu: the three-kernel stage of small problems (pyh_stage_split.cuh)
 SplitReconFn pick_split_recon(int l, int p);
 SplitFluxFn pick_split_flux(int f, int p);
-void launch_split_update(dim3 grid, cudaStream_t st, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-                         const Control* ctl, Control* ctl_out, const Consts C);
+cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                               const unsigned cur, const Control* ctl, const Consts C);
+cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                              const unsigned cur, const Control* ctl, const Consts C);
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+                                const Control* ctl, Control* ctl_out, const Consts C);
 }
 
 namespace {
@@ -281,13 +285,11 @@ int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
     const unsigned nb = (unsigned)c->blocks.size();
     SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon);
     SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon);
-    k1<<<dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), kSplitReconThreads, 0, st>>>(c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C);
-    CU(cudaGetLastError());
+    static const bool pdl = getenv("PYH_NO_PDL") == nullptr;   // programmatic dependent launch (pyh_stage_split.cuh); PYH_NO_PDL=1: plain stream order (A/B)
+    CU(launch_split_recon(k1, dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
     const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
-    k2<<<dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), kSplitFluxThreads, 0, st>>>(c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C);
-    CU(cudaGetLastError());
-    launch_split_update(dim3(cdiv((long long)nx * ny, kSplitUpdateThreads), 1, nb), st, c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C);
-    CU(cudaGetLastError());
+    CU(launch_split_flux(k2, dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
+    CU(launch_split_update(dim3(cdiv((long long)nx * ny, kSplitUpdateThreads), 1, nb), st, pdl, c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C));
     c->launches += 3;
     return 0;
 }

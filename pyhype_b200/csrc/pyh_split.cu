@@ -1,5 +1,6 @@
 // Instantiations of the three-kernel stage of small problems (pyh_stage_split.cuh): a translation unit of its own so that it
 // compiles in parallel with the fused stage kernels (see __graft_entry__.build).
+#include <cstring>
 #include "pyh_stage_split.cuh"
 
 namespace pyh {
@@ -23,8 +24,32 @@ SplitFluxFn pick_split_flux(int f, int p) {
         default: return fpick<2>(p);
     }
 }
-void launch_split_update(dim3 grid, cudaStream_t st, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-                         const Control* ctl, Control* ctl_out, const Consts C) {
-    k_split_update<<<grid, kSplitUpdateThreads, 0, st>>>(blks, lay, po, plan, ctl, ctl_out, C);
+// cudaLaunchKernelEx with (pdl) or without programmatic stream serialization (pyh_stage_split.cuh: pdl_wait / pdl_trigger)
+template <typename... P, typename... A>
+static cudaError_t launch_ex(void (*fn)(P...), dim3 grid, int threads, cudaStream_t st, bool pdl, A... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fn, args...);
+}
+cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                               const unsigned cur, const Control* ctl, const Consts C) {
+    return launch_ex(fn, grid, kSplitReconThreads, st, pdl, blks, lay, po, cur, ctl, C);
+}
+cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                              const unsigned cur, const Control* ctl, const Consts C) {
+    return launch_ex(fn, grid, kSplitFluxThreads, st, pdl, blks, lay, po, cur, ctl, C);
+}
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+                                const Control* ctl, Control* ctl_out, const Consts C) {
+    return launch_ex(k_split_update, grid, kSplitUpdateThreads, st, pdl, blks, lay, po, plan, ctl, ctl_out, C);
 }
 }  // namespace pyh

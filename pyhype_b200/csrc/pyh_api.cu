@@ -49,11 +49,12 @@ MarchFn pick_march_nq3(int f, int l, int p);
 // pyh_split.cu: the three-kernel stage of small problems (pyh_stage_split.cuh)
 SplitReconFn pick_split_recon(int l, int p);
 SplitFluxFn pick_split_flux(int f, int p);
-cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+struct SplitLaunchOpts { bool pdl; const void* win_base; size_t win_bytes; float win_hit; };   // PDL chaining + persisting-L2 window over the scratch planes
+cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                                const unsigned cur, const Control* ctl, const Consts C);
-cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                               const unsigned cur, const Control* ctl, const Consts C);
-cudaError_t launch_split_update(dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
                                 const Control* ctl, Control* ctl_out, const Consts C);
 }
 
@@ -97,6 +98,9 @@ struct Ctx {
     bool split_ready = false;        // scratch planes of the split path allocated (eligible context)
     bool path_tuned = false;         // tune_stage_path has run (first pyh_run)
     double tune_ms[2] = {0.0, 0.0};  // what it measured: ms per stage launch, fused / split
+    double* d_aux = nullptr;         // scratch planes of the split path, all blocks in ONE allocation (so that one L2 access-policy window covers them)
+    size_t aux_bytes = 0;
+    float aux_hit_ratio = 0.f;       // > 0: the split kernels are launched with a persisting-L2 window over d_aux
     bool push_ok = false;            // ghost cells are written by the stage kernel itself (plan.push_ghost): no k_ghost / k_pack_halo per stage
     // asynchronous state streaming (pyh_upload_state_async & co)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -285,7 +289,10 @@ int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
     const unsigned nb = (unsigned)c->blocks.size();
     SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon);
     SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon);
-    static const bool pdl = getenv("PYH_NO_PDL") == nullptr;   // programmatic dependent launch (pyh_stage_split.cuh); PYH_NO_PDL=1: plain stream order (A/B)
+    static const bool use_pdl = getenv("PYH_NO_PDL") == nullptr;   // programmatic dependent launch (pyh_stage_split.cuh); PYH_NO_PDL=1: plain stream order (A/B)
+    int max_window = 0;
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->cfg.device);
+    const SplitLaunchOpts pdl = {use_pdl, c->d_aux, std::min<size_t>(c->aux_bytes, (size_t)std::max(max_window, 0)), c->aux_hit_ratio};
     CU(launch_split_recon(k1, dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
     const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
     CU(launch_split_flux(k2, dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
@@ -671,9 +678,30 @@ int pyh_finalize(void* ctx) {
     }
     c->split_ready = split_eligible(c);
     c->use_split = c->split_ready && getenv("PYH_SPLIT") != nullptr;   // forced; otherwise decided by measurement at the first pyh_run
-    if (c->split_ready)   // limited face states + face fluxes between the three kernels of a stage (L2-resident at the sizes that take this path)
-        for (auto& hb : c->blocks)
-            if (int rc = dalloc(hb, &hb.dev.aux, (long long)kSplitPlanes * c->lay.plane, true)) return rc;
+    if (c->split_ready) {
+        // limited face states + face fluxes between the three kernels of a stage: written once, read once, then dead.  One
+        // allocation for all blocks, marked PERSISTING in the L2 for the split kernels (launch attribute, pyh_split.cu): what a
+        // stage streams through (state, geometry) can then not evict what the next kernel is about to read.  If the scratch is
+        // larger than the persisting carve-out the driver grants, a matching fraction of its lines is kept (hitRatio).
+        const size_t per = (size_t)kSplitPlanes * c->lay.plane * sizeof(double);
+        c->aux_bytes = per * c->blocks.size();
+        cudaError_t e = cudaMalloc(&c->d_aux, c->aux_bytes);
+        if (e != cudaSuccess) return set_err(PYH_ERR_NOMEM, "cudaMalloc of %zu bytes of stage scratch failed: %s", c->aux_bytes, cudaGetErrorString(e));
+        CU(cudaMemset(c->d_aux, 0, c->aux_bytes));
+        for (size_t b = 0; b < c->blocks.size(); ++b) c->blocks[b].dev.aux = c->d_aux + b * (per / sizeof(double));
+        if (!getenv("PYH_NO_L2_PERSIST")) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->cfg.device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->cfg.device);
+            const size_t want = std::min<size_t>(c->aux_bytes, (size_t)std::max(max_persist, 0));
+            if (want > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                size_t got = 0;
+                cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+                const size_t window = std::min<size_t>(c->aux_bytes, (size_t)max_window);
+                c->aux_hit_ratio = (float)std::min(1.0, (double)got / (double)window);
+            } else cudaGetLastError();
+        }
+    }
     std::vector<BlkDev> tmp;
     for (auto& hb : c->blocks) tmp.push_back(hb.dev);
     CU(cudaMalloc(&c->d_blks, std::max<size_t>(tmp.size(), 1) * sizeof(BlkDev)));
@@ -703,6 +731,7 @@ int pyh_destroy(void* ctx) {
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_dts) cudaFree(c->d_dts);
     if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->d_aux) cudaFree(c->d_aux);
     if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
     if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
     if (c->ev_in_done) cudaEventDestroy(c->ev_in_done);

@@ -24,31 +24,47 @@ SplitFluxFn pick_split_flux(int f, int p) {
         default: return fpick<2>(p);
     }
 }
-// cudaLaunchKernelEx with (pdl) or without programmatic stream serialization (pyh_stage_split.cuh: pdl_wait / pdl_trigger)
+struct SplitLaunchOpts { bool pdl; const void* win_base; size_t win_bytes; float win_hit; };   // same as in pyh_api.cu
+// cudaLaunchKernelEx with / without programmatic stream serialization (pyh_stage_split.cuh: pdl_wait / pdl_trigger) and with / without
+// a persisting-L2 access-policy window over the stage scratch (written by one kernel of the stage, read by the next)
 template <typename... P, typename... A>
-static cudaError_t launch_ex(void (*fn)(P...), dim3 grid, int threads, cudaStream_t st, bool pdl, A... args) {
+static cudaError_t launch_ex(void (*fn)(P...), dim3 grid, int threads, cudaStream_t st, const SplitLaunchOpts& o, A... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    memset(at, 0, sizeof(at));
+    unsigned n = 0;
+    if (o.pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (o.win_hit > 0.f && o.win_bytes > 0) {
+        at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(o.win_base);
+        at[n].val.accessPolicyWindow.num_bytes = o.win_bytes;
+        at[n].val.accessPolicyWindow.hitRatio = o.win_hit;
+        at[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++n;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, fn, args...);
 }
-cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                                const unsigned cur, const Control* ctl, const Consts C) {
     return launch_ex(fn, grid, kSplitReconThreads, st, pdl, blks, lay, po, cur, ctl, C);
 }
-cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                               const unsigned cur, const Control* ctl, const Consts C) {
     return launch_ex(fn, grid, kSplitFluxThreads, st, pdl, blks, lay, po, cur, ctl, C);
 }
-cudaError_t launch_split_update(dim3 grid, cudaStream_t st, bool pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
                                 const Control* ctl, Control* ctl_out, const Consts C) {
     return launch_ex(k_split_update, grid, kSplitUpdateThreads, st, pdl, blks, lay, po, plan, ctl, ctl_out, C);
 }

@@ -34,8 +34,9 @@ namespace pyh {
 // kernel needs ALL of its predecessor's output.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a kernel's
 // thread blocks may be scheduled while the predecessor's last wave is still running; pdl_wait() then blocks until the
 // predecessor has completed and its writes are visible (everything older is complete transitively: each kernel waits first
-// thing), and pdl_trigger() lets the successor start its own launch.  What overlaps is launch latency and block scheduling,
-// ~2 us per boundary, 13 boundaries per RK4 step.  Without the launch attribute both are no-ops.
+// thing, before it touches memory, so there is no write-after-read hazard either), and pdl_trigger() lets the successor start
+// its own launch.  What overlaps is launch latency and block scheduling: 0.8 us per boundary measured, 13 boundaries per RK4
+// step (explosion_multi 0.168 -> 0.158 ms/step).  Without the launch attribute both are no-ops.
 __device__ __forceinline__ void pdl_wait() {
 #if !defined(PYH_HOST_TWIN)
     asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -100,7 +100,9 @@ struct Ctx {
     double tune_ms[2] = {0.0, 0.0};  // what it measured: ms per stage launch, fused / split
     double* d_aux = nullptr;         // scratch planes of the split path, all blocks in ONE allocation (so that one L2 access-policy window covers them)
     size_t aux_bytes = 0;
-    float aux_hit_ratio = 0.f;       // > 0: the split kernels are launched with a persisting-L2 window over d_aux
+    float aux_hit_ratio = 0.f;       // > 0: the split kernels are launched with a persisting-L2 window over [win_base, win_base + win_bytes)
+    const void* win_base = nullptr;
+    size_t win_bytes = 0;
     bool push_ok = false;            // ghost cells are written by the stage kernel itself (plan.push_ghost): no k_ghost / k_pack_halo per stage
     // asynchronous state streaming (pyh_upload_state_async & co)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -290,9 +292,7 @@ int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
     SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon);
     SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon);
     static const bool use_pdl = getenv("PYH_NO_PDL") == nullptr;   // programmatic dependent launch (pyh_stage_split.cuh); PYH_NO_PDL=1: plain stream order (A/B)
-    int max_window = 0;
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->cfg.device);
-    const SplitLaunchOpts pdl = {use_pdl, c->d_aux, std::min<size_t>(c->aux_bytes, (size_t)std::max(max_window, 0)), c->aux_hit_ratio};
+    const SplitLaunchOpts pdl = {use_pdl, c->win_base, c->win_bytes, c->aux_hit_ratio};
     CU(launch_split_recon(k1, dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
     const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
     CU(launch_split_flux(k2, dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
@@ -683,22 +683,31 @@ int pyh_finalize(void* ctx) {
         // allocation for all blocks, marked PERSISTING in the L2 for the split kernels (launch attribute, pyh_split.cu): what a
         // stage streams through (state, geometry) can then not evict what the next kernel is about to read.  If the scratch is
         // larger than the persisting carve-out the driver grants, a matching fraction of its lines is kept (hitRatio).
-        const size_t per = (size_t)kSplitPlanes * c->lay.plane * sizeof(double);
-        c->aux_bytes = per * c->blocks.size();
+        const size_t nb = c->blocks.size();
+        const size_t fs_per = (size_t)kSplitStatePlanes * c->lay.plane, fx_per = (size_t)kSplitFluxPlanes * c->lay.plane;   // doubles
+        const size_t fs_bytes = fs_per * nb * sizeof(double), fx_bytes = fx_per * nb * sizeof(double);
+        c->aux_bytes = fs_bytes + fx_bytes;
         cudaError_t e = cudaMalloc(&c->d_aux, c->aux_bytes);
         if (e != cudaSuccess) return set_err(PYH_ERR_NOMEM, "cudaMalloc of %zu bytes of stage scratch failed: %s", c->aux_bytes, cudaGetErrorString(e));
         CU(cudaMemset(c->d_aux, 0, c->aux_bytes));
-        for (size_t b = 0; b < c->blocks.size(); ++b) c->blocks[b].dev.aux = c->d_aux + b * (per / sizeof(double));
+        double* const fx0 = c->d_aux + fs_per * nb;   // layout: [face states of every block][face fluxes of every block]
+        for (size_t b = 0; b < nb; ++b) { c->blocks[b].dev.aux = c->d_aux + b * fs_per; c->blocks[b].dev.aux_fx = fx0 + b * fx_per; }
+        // ... but only if ALL of it fits the persisting carve-out the device grants (B200: 79 MB of the 126 MB L2).  Measured
+        // (profiles/r02y_l2_persist_ab.txt): explosion_multi, 36 MB of scratch, 0.158 -> 0.150 ms/step; a PARTIAL window (DMR: 193 MB,
+        // hitRatio 0.43) thrashes, 0.44 -> 0.79; a window over the flux planes alone (64 MB for DMR) changes nothing (-1.8 % / +2.5 %).
         if (!getenv("PYH_NO_L2_PERSIST")) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->cfg.device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->cfg.device);
-            const size_t want = std::min<size_t>(c->aux_bytes, (size_t)std::max(max_persist, 0));
-            if (want > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            const size_t cap = (size_t)std::max(std::min(max_persist, max_window), 0);
+            const void* base = nullptr;
+            size_t bytes = 0;
+            if (c->aux_bytes <= cap) { base = c->d_aux; bytes = c->aux_bytes; }
+            if (bytes > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) == cudaSuccess) {
                 size_t got = 0;
                 cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
-                const size_t window = std::min<size_t>(c->aux_bytes, (size_t)max_window);
-                c->aux_hit_ratio = (float)std::min(1.0, (double)got / (double)window);
+                if (got >= bytes) { c->aux_hit_ratio = 1.0f; c->win_base = base; c->win_bytes = bytes; }
+                else cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
             } else cudaGetLastError();
         }
     }
@@ -731,6 +740,10 @@ int pyh_destroy(void* ctx) {
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_dts) cudaFree(c->d_dts);
     if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->aux_hit_ratio > 0.f) {   // give the persisting carve-out back: later contexts of this process want the whole L2
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     if (c->d_aux) cudaFree(c->d_aux);
     if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
     if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }

@@ -86,7 +86,8 @@ struct BlkDev {
     double* base;                 // the block's slab
     double* dbg;                  // 4 planes: residual test hook (allocated on demand)
     double* dbgG;                 // 12 planes: gx[4], gy[4], phi[4] (allocated on demand)
-    double* aux;                  // 24 planes: limited face states + face fluxes of the three-kernel stage of small problems (pyh_stage_split.cuh), else null
+    double* aux;                  // 16 planes: limited face states (E, W, N, S x 4 variables) between the kernels of the split stage (pyh_stage_split.cuh), else null
+    double* aux_fx;               // 8 planes: face fluxes (vertical, horizontal x 4) of the split stage; the flux planes of all blocks are contiguous
     const double* dir_recon[4];   // Dirichlet strips in reconstruction variables (edge_len x 4, AoS)
     const double* dir_cons[4];    // Dirichlet strips in conservative variables
     int bc[4];

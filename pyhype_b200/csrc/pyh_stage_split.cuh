@@ -252,7 +252,7 @@ k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffse
     if (i >= (horiz ? ny + 1 : ny)) return;
     double F[4];
     split_face_flux<FLUX, PRIM>(B, B.base + cur, B.base, B.aux, lay, po, C, horiz, i, j, F);
-    double* __restrict__ const out = B.aux + (16 + (horiz ? 4 : 0)) * (size_t)lay.plane + lay.at(i, j);
+    double* __restrict__ const out = B.aux_fx + (horiz ? 4 : 0) * (size_t)lay.plane + lay.at(i, j);
 #pragma unroll
     for (int k = 0; k < 4; ++k) out[k * (size_t)lay.plane] = F[k];
 }
@@ -270,7 +270,7 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
     const BlkDev& B = blks[blockIdx.z];
     double* __restrict__ const base = B.base;
     const double* __restrict__ const G = B.base;
-    const double* __restrict__ const FX = B.aux + 16 * (size_t)lay.plane;
+    const double* __restrict__ const FX = B.aux_fx;
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
     const unsigned n = blockIdx.x * (unsigned)kSplitUpdateThreads + threadIdx.x;

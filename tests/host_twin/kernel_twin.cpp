@@ -149,7 +149,7 @@ struct Twin {
             D.base = slab;
             D.dbg = dbg[b].data();
             D.dbgG = dbgG[b].data();
-            if (splitpath) { aux[b].assign((size_t)kSplitPlanes * lay.plane, 0.0); D.aux = aux[b].data(); }
+            if (splitpath) { aux[b].assign((size_t)kSplitPlanes * lay.plane, 0.0); D.aux = aux[b].data(); D.aux_fx = D.aux + (size_t)kSplitStatePlanes * lay.plane; }
             for (int s = 0; s < 4; ++s) {
                 D.bc[s] = bc[4 * b + s];
                 D.nbr[s] = nbr[4 * b + s];

@@ -347,6 +347,11 @@ int tune_stage_path(Ctx* c) {
     c->launches = l0;                                   // tuning launches are not part of any step
     c->tune_ms[0] = ms[0] / kReps; c->tune_ms[1] = ms[1] / kReps;
     c->use_split = ms[1] < 0.97f * ms[0];               // ties go to the fused kernel
+    if (!c->use_split && c->aux_hit_ratio > 0.f) {      // the fused kernel it is: it gets the whole L2 back
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        c->aux_hit_ratio = 0.f;
+    }
     return 0;
 }
 
@@ -681,8 +686,7 @@ int pyh_finalize(void* ctx) {
     if (c->split_ready) {
         // limited face states + face fluxes between the three kernels of a stage: written once, read once, then dead.  One
         // allocation for all blocks, marked PERSISTING in the L2 for the split kernels (launch attribute, pyh_split.cu): what a
-        // stage streams through (state, geometry) can then not evict what the next kernel is about to read.  If the scratch is
-        // larger than the persisting carve-out the driver grants, a matching fraction of its lines is kept (hitRatio).
+        // stage streams through (state, geometry) can then not evict what the next kernel is about to read ...
         const size_t nb = c->blocks.size();
         const size_t fs_per = (size_t)kSplitStatePlanes * c->lay.plane, fx_per = (size_t)kSplitFluxPlanes * c->lay.plane;   // doubles
         const size_t fs_bytes = fs_per * nb * sizeof(double), fx_bytes = fx_per * nb * sizeof(double);

@@ -47,8 +47,8 @@ MarchFn pick_march_nq1(int f, int l, int p);
 MarchFn pick_march_nq2(int f, int l, int p);
 MarchFn pick_march_nq3(int f, int l, int p);
 // pyh_split.cu: the three-kernel stage of small problems (pyh_stage_split.cuh)
-SplitReconFn pick_split_recon(int l, int p);
-SplitFluxFn pick_split_flux(int f, int p);
+SplitReconFn pick_split_recon(int l, int p, bool dense);
+SplitFluxFn pick_split_flux(int f, int p, bool dense);
 struct SplitLaunchOpts { bool pdl; const void* win_base; size_t win_bytes; float win_hit; };   // PDL chaining + persisting-L2 window over the scratch planes
 cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                                const unsigned cur, const Control* ctl, const Consts C);
@@ -289,8 +289,9 @@ int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
     if (c->blocks.empty()) return 0;
     const int nx = c->lay.nx, ny = c->lay.ny;
     const unsigned nb = (unsigned)c->blocks.size();
-    SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon);
-    SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon);
+    const bool dense = (long long)nx * ny * nb > kSplitDenseCells;   // many waves: the high-occupancy builds of the kernels (pyh_split.cu)
+    SplitReconFn k1 = pick_split_recon(c->cfg.limiter, c->cfg.recon, dense);
+    SplitFluxFn k2 = pick_split_flux(c->cfg.flux, c->cfg.recon, dense);
     static const bool use_pdl = getenv("PYH_NO_PDL") == nullptr;   // programmatic dependent launch (pyh_stage_split.cuh); PYH_NO_PDL=1: plain stream order (A/B)
     const SplitLaunchOpts pdl = {use_pdl, c->win_base, c->win_bytes, c->aux_hit_ratio};
     CU(launch_split_recon(k1, dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));

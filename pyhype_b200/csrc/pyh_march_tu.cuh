@@ -35,6 +35,7 @@ constexpr int kSplitFluxThreads = 128;
 constexpr int kSplitUpdateThreads = 256;
 constexpr int kSplitStatePlanes = 16, kSplitFluxPlanes = 8;  // FS: E, W, N, S face states x 4 variables; FX: vertical, horizontal face fluxes x 4
 constexpr int kSplitPlanes = kSplitStatePlanes + kSplitFluxPlanes;
+constexpr long long kSplitDenseCells = 500000;               // above: the split kernels' high-occupancy builds (explosion_multi is 180 k cells, DMR 1 M)
 constexpr long long kSplitMaxCells = 4500000;               // above: always the fused kernel (the scratch planes cost 192 B per cell; 8 x 1024^2 was 20 % slower split)
 // shared-memory doubles per thread for NQ quadrature points per face:
 // sQ[3][4], sFE[2][NQ][4], sIW[2][4], sQN[2][NQ][4], sIS[4], sQW[NQ][4], sQS[NQ][4]

@@ -4,24 +4,35 @@
 #include "pyh_stage_split.cuh"
 
 namespace pyh {
+// Occupancy targets (launch bounds), measured on the B200 (profiles/r02z_split_occupancy_ab.txt).  Problems of many waves are
+// throughput-bound and gain from more resident warps even at the price of a few spilled registers (`dense`: recon 4 x 256 threads at
+// 64 registers, flux 8 x 128 at 64; DMR 0.416 -> 0.405 ms/step); problems of one or two waves are latency-bound and lose
+// (explosion_multi 0.153 -> 0.159), they keep recon 3 x 256 and flux 6 x 128 at 80 registers.  For the HLLL flux the step from
+// ptxas' own choice (122 registers, 4 x 128) to 80 registers alone was worth 5 % on DMR.
 template <int L>
-static SplitReconFn rpick(int p) { return p ? k_split_recon<L, 1> : k_split_recon<L, 0>; }
+static SplitReconFn rpick(int p, bool dense) {
+    if (dense) return p ? k_split_recon<L, 1, 4> : k_split_recon<L, 0, 4>;
+    return p ? k_split_recon<L, 1, 3> : k_split_recon<L, 0, 3>;
+}
 template <int F>
-static SplitFluxFn fpick(int p) { return p ? k_split_flux<F, 1> : k_split_flux<F, 0>; }
+static SplitFluxFn fpick(int p, bool dense) {
+    if (dense) return p ? k_split_flux<F, 1, 8> : k_split_flux<F, 0, 8>;
+    return p ? k_split_flux<F, 1, 6> : k_split_flux<F, 0, 6>;
+}
 
-SplitReconFn pick_split_recon(int l, int p) {
+SplitReconFn pick_split_recon(int l, int p, bool dense) {
     switch (l) {
-        case 0: return rpick<0>(p);
-        case 1: return rpick<1>(p);
-        case 2: return rpick<2>(p);
-        default: return rpick<3>(p);
+        case 0: return rpick<0>(p, dense);
+        case 1: return rpick<1>(p, dense);
+        case 2: return rpick<2>(p, dense);
+        default: return rpick<3>(p, dense);
     }
 }
-SplitFluxFn pick_split_flux(int f, int p) {
+SplitFluxFn pick_split_flux(int f, int p, bool dense) {
     switch (f) {
-        case 0: return fpick<0>(p);
-        case 1: return fpick<1>(p);
-        default: return fpick<2>(p);
+        case 0: return fpick<0>(p, dense);
+        case 1: return fpick<1>(p, dense);
+        default: return fpick<2>(p, dense);
     }
 }
 struct SplitLaunchOpts { bool pdl; const void* win_base; size_t win_bytes; float win_hit; };   // same as in pyh_api.cu

@@ -66,8 +66,8 @@ __device__ __forceinline__ void split_to_recon(double q[4], const Consts& C) {
 // ---- 1: gradient + limiter + limited face states ------------------------------------------------------------------------
 // (Requesting the cell's 21 geometry values BEFORE the tile of states is staged, so that their latency overlaps the staging and
 // the barrier, was measured and lost: explosion_multi 0.1726 vs 0.1676 ms/step, profiles/r02p_split_stage_merged_ab.txt.)
-template <int LIM, int PRIM>
-__global__ void __launch_bounds__(kSplitReconThreads, 3)
+template <int LIM, int PRIM, int MINB>
+__global__ void __launch_bounds__(kSplitReconThreads, MINB)
 k_split_recon(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
               const Consts C) {
     pdl_wait();
@@ -236,8 +236,8 @@ __device__ __forceinline__ void split_face_flux(const BlkDev& B, const double* _
 
 // One thread per face.  blockIdx.y = 0: vertical faces (i, J), i in [0, ny), J in [0, nx] (the west face of cell (i, J));
 // blockIdx.y = 1: horizontal faces (I, j), I in [0, ny], j in [0, nx) (the south face of cell (I, j)).
-template <int FLUX, int PRIM>
-__global__ void __launch_bounds__(kSplitFluxThreads)
+template <int FLUX, int PRIM, int MINB>
+__global__ void __launch_bounds__(kSplitFluxThreads, MINB)
 k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
              const Consts C) {
     pdl_wait();

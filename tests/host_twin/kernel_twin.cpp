@@ -50,20 +50,20 @@ static MarchFn pick(int f, int l, int p, int nq) {
 
 // the three-kernel stage of small problems (pyh_stage_split.cuh), same set of instantiations
 static SplitReconFn pick_recon(int l, int p) {
-    if (l == 0) return p ? k_split_recon<0, 1> : k_split_recon<0, 0>;
+    if (l == 0) return p ? k_split_recon<0, 1, 3> : k_split_recon<0, 0, 3>;
     if (p) return nullptr;
-    if (l == 1) return k_split_recon<1, 0>;
-    if (l == 2) return k_split_recon<2, 0>;
-    return k_split_recon<3, 0>;
+    if (l == 1) return k_split_recon<1, 0, 3>;
+    if (l == 2) return k_split_recon<2, 0, 3>;
+    return k_split_recon<3, 0, 3>;
 }
 static SplitFluxFn pick_flux(int f, int p) {
     switch (2 * f + p) {
-        case 0: return k_split_flux<0, 0>;
-        case 1: return k_split_flux<0, 1>;
-        case 2: return k_split_flux<1, 0>;
-        case 3: return k_split_flux<1, 1>;
-        case 4: return k_split_flux<2, 0>;
-        default: return k_split_flux<2, 1>;
+        case 0: return k_split_flux<0, 0, 1>;
+        case 1: return k_split_flux<0, 1, 1>;
+        case 2: return k_split_flux<1, 0, 1>;
+        case 3: return k_split_flux<1, 1, 1>;
+        case 4: return k_split_flux<2, 0, 1>;
+        default: return k_split_flux<2, 1, 1>;
     }
 }
 

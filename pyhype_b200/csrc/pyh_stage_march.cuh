@@ -67,12 +67,11 @@ static __device__ __noinline__ void hook_store4(double* p, size_t i0, size_t str
 // is one kernel launch per stage (and the pack launch before every NCCL exchange).  Cell (i, j) of the stage's output
 // buffer `dst`, sides selected by `ns` (north / south) or east / west.  (Called from the tail of the kernel: a call inside
 // the row loop, however rarely taken, cost the loop 12 % through the registers it pinned -- measured.)
-static __device__ __forceinline__ void push_ghost_cell(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
-                                                       const unsigned dst, const int i, const int j, const bool ns) {
+static __device__ __forceinline__ void push_ghost_values(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
+                                                         const unsigned dst, const int i, const int j, const bool ns,
+                                                         const double u0, const double u1, const double u2, const double u3) {
     const int nx = lay.nx, ny = lay.ny;
     const unsigned PL = lay.plane;
-    const double* u = B.base + dst + lay.at(i, j);
-    const double u0 = u[0], u1 = u[PL], u2 = u[2 * PL], u3 = u[3 * PL];
 #pragma unroll 1
     for (int side = ns ? PYH_NORTH : PYH_EAST; side <= (ns ? PYH_SOUTH : PYH_WEST); ++side) {
         int gi, gj, oi, oj, fi, fj, idx;      // own ghost cell, the neighbour's mirror ghost cell, the boundary face, index along the edge
@@ -102,6 +101,13 @@ static __device__ __forceinline__ void push_ghost_cell(const BlkDev* __restrict_
             g[0] = q0; g[1] = q1; g[2] = q2; g[3] = q3;
         }
     }
+}
+// ... the same for a cell whose new value is re-read from the output buffer (the fused kernel: its tail runs after the row loop)
+static __device__ __forceinline__ void push_ghost_cell(const BlkDev* __restrict__ blks, const BlkDev& B, const Layout lay, const PlaneOffsets po,
+                                                       const unsigned dst, const int i, const int j, const bool ns) {
+    const unsigned PL = lay.plane;
+    const double* u = B.base + dst + lay.at(i, j);
+    push_ghost_values(blks, B, lay, po, dst, i, j, ns, u[0], u[PL], u[2 * PL], u[3 * PL]);
 }
 
 typedef std::integral_constant<bool, true> FastTag;

@@ -280,6 +280,20 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
     if (live) {
         const unsigned o = lay.at(i, j);
         const int nt_ = plan.ntargets;
+#if !defined(PYH_HOST_TWIN)
+        if (plan.push_ghost) {   // edge cells: cos / sin of their boundary faces (reflection walls) into the L1 now, needed by the ghost push at the end
+            if (i == 0 || i == ny - 1) {
+                const unsigned of = lay.at(i == 0 ? 0 : ny, j);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(G + po.ch + of));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(G + po.sh + of));
+            }
+            if (j == 0 || j == nx - 1) {
+                const unsigned of = lay.at(i, j == 0 ? 0 : nx);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(G + po.cv + of));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(G + po.sv + of));
+            }
+        }
+#endif
         const double a = PYH_RO(G[po.A + o]);
         double dI[4], s0[4], s1[4];
 #pragma unroll
@@ -354,8 +368,9 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
         if (plan.push_ghost && nt_ > 0) {
             // ghost cells mirroring an edge cell this thread has just written (target 0 is the stage's output state)
             const unsigned dst = plan.t[0].dst;
-            if (i == 0 || i == ny - 1) push_ghost_cell(blks, B, lay, po, dst, i, j, true);
-            if (j == 0 || j == nx - 1) push_ghost_cell(blks, B, lay, po, dst, i, j, false);
+            // from registers (no re-read of the value just stored); the wall geometry was prefetched at the top
+            if (i == 0 || i == ny - 1) push_ghost_values(blks, B, lay, po, dst, i, j, true, un[0], un[1], un[2], un[3]);
+            if (j == 0 || j == nx - 1) push_ghost_values(blks, B, lay, po, dst, i, j, false, un[0], un[1], un[2], un[3]);
         }
     }
     if (plan.fuse_dt) {   // block minimum -> one atomicMin per thread block (quad_block.py:436: min over cells; Solver.get_dt: over blocks)

@@ -54,8 +54,8 @@ cudaError_t launch_split_recon(SplitReconFn fn, dim3 grid, cudaStream_t st, Spli
                                const unsigned cur, const Control* ctl, const Consts C);
 cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
                               const unsigned cur, const Control* ctl, const Consts C);
-cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-                                const Control* ctl, Control* ctl_out, const Consts C);
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, bool dense, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                                const StagePlan plan, const Control* ctl, Control* ctl_out, const Consts C);
 }
 
 namespace {
@@ -297,7 +297,7 @@ int launch_stage_split(Ctx* c, const StagePlan& plan, cudaStream_t st) {
     CU(launch_split_recon(k1, dim3(cdiv(nx, kSplitTX), cdiv(ny, kSplitTY), nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
     const long long nfaces = std::max((long long)(nx + 1) * ny, (long long)nx * (ny + 1));
     CU(launch_split_flux(k2, dim3(cdiv(nfaces, kSplitFluxThreads), 2, nb), st, pdl, c->d_blks, c->lay, c->po, plan.cur, c->d_ctl, c->C));
-    CU(launch_split_update(dim3(cdiv((long long)nx * ny, kSplitUpdateThreads), 1, nb), st, pdl, c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C));
+    CU(launch_split_update(dim3(cdiv((long long)nx * ny, kSplitUpdateThreads), 1, nb), st, pdl, dense, c->d_blks, c->lay, c->po, plan, c->d_ctl, c->d_ctl, c->C));
     c->launches += 3;
     return 0;
 }

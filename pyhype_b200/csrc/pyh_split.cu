@@ -75,8 +75,9 @@ cudaError_t launch_split_flux(SplitFluxFn fn, dim3 grid, cudaStream_t st, SplitL
                               const unsigned cur, const Control* ctl, const Consts C) {
     return launch_ex(fn, grid, kSplitFluxThreads, st, pdl, blks, lay, po, cur, ctl, C);
 }
-cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, const BlkDev* blks, const Layout lay, const PlaneOffsets po, const StagePlan plan,
-                                const Control* ctl, Control* ctl_out, const Consts C) {
-    return launch_ex(k_split_update, grid, kSplitUpdateThreads, st, pdl, blks, lay, po, plan, ctl, ctl_out, C);
+cudaError_t launch_split_update(dim3 grid, cudaStream_t st, SplitLaunchOpts pdl, bool dense, const BlkDev* blks, const Layout lay, const PlaneOffsets po,
+                                const StagePlan plan, const Control* ctl, Control* ctl_out, const Consts C) {
+    if (dense) return launch_ex(k_split_update<4>, grid, kSplitUpdateThreads, st, pdl, blks, lay, po, plan, ctl, ctl_out, C);
+    return launch_ex(k_split_update<5>, grid, kSplitUpdateThreads, st, pdl, blks, lay, po, plan, ctl, ctl_out, C);
 }
 }  // namespace pyh

@@ -70,15 +70,15 @@ template <int LIM, int PRIM, int MINB>
 __global__ void __launch_bounds__(kSplitReconThreads, MINB)
 k_split_recon(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
               const Consts C) {
-    pdl_wait();
-    pdl_trigger();
-    if (!ctl->active) return;
     constexpr int TX = kSplitTX, TY = kSplitTY, SX = TX + 2, SY = TY + 2;
     __shared__ double sq[4][SY][SX];                        // reconstruction variables of the tile and its one-cell frame
-    const BlkDev& B = blks[blockIdx.z];
+    const BlkDev& B = blks[blockIdx.z];                     // the block table is constant for the life of the context: read ahead of the wait
     const double* __restrict__ const U = B.base + cur;
     const double* __restrict__ const G = B.base;
     double* __restrict__ const FS = B.aux;
+    pdl_wait();
+    pdl_trigger();
+    if (!ctl->active) return;
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
     const int t = threadIdx.x;
@@ -240,10 +240,13 @@ template <int FLUX, int PRIM, int MINB>
 __global__ void __launch_bounds__(kSplitFluxThreads, MINB)
 k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const unsigned cur, const Control* __restrict__ ctl,
              const Consts C) {
+    const BlkDev& B = blks[blockIdx.z];                     // constant for the life of the context: read ahead of the wait
+    double* const aux_fx = B.aux_fx;
+    const double* const aux_fs = B.aux;
+    const double* const slab = B.base;
     pdl_wait();
     pdl_trigger();
     if (!ctl->active) return;
-    const BlkDev& B = blks[blockIdx.z];
     const int nx = lay.nx, ny = lay.ny;
     const bool horiz = blockIdx.y != 0;
     const int W = horiz ? nx : nx + 1;
@@ -251,37 +254,47 @@ k_split_flux(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffse
     const int i = (int)(n / (unsigned)W), j = (int)(n - (unsigned)i * (unsigned)W);
     if (i >= (horiz ? ny + 1 : ny)) return;
     double F[4];
-    split_face_flux<FLUX, PRIM>(B, B.base + cur, B.base, B.aux, lay, po, C, horiz, i, j, F);
-    double* __restrict__ const out = B.aux_fx + (horiz ? 4 : 0) * (size_t)lay.plane + lay.at(i, j);
+    split_face_flux<FLUX, PRIM>(B, slab + cur, slab, aux_fs, lay, po, C, horiz, i, j, F);
+    double* __restrict__ const out = aux_fx + (horiz ? 4 : 0) * (size_t)lay.plane + lay.at(i, j);
 #pragma unroll
     for (int k = 0; k < 4; ++k) out[k * (size_t)lay.plane] = F[k];
 }
 
 // ---- 3: residual + RK partial sums (+ CFL minimum of the new state, ghost push) ------------------------------------------
-// One thread per cell, every load issued before the first use (the kernel is a chain of dependent memory round trips, not
-// arithmetic), all cells of explosion_multi resident at once (5 x 256 threads per SM).
-__global__ void __launch_bounds__(kSplitUpdateThreads, 5)
+// One thread per cell.  The kernel is a chain of dependent memory round trips, not arithmetic, so everything is requested as
+// early as it can be: the block table (constant for the life of the context) before the wait on the predecessor, every operand
+// -- including the time loop's `active` flag and the RK coefficients -- before the first use, and the early exit of an inactive
+// step is taken once all of them are in flight.  All cells of explosion_multi are resident at once (5 x 256 threads per SM).
+template <int MINB>   // 5: 48 registers, all of explosion_multi in one wave; 4: 64 registers, every operand of a cell in flight at once
+__global__ void __launch_bounds__(kSplitUpdateThreads, MINB)
 k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOffsets po, const StagePlan plan, const Control* __restrict__ ctl,
                Control* __restrict__ ctl_out, const Consts C) {
-    pdl_wait();
-    pdl_trigger();
-    if (!ctl->active) return;
     __shared__ double sDT[kSplitUpdateThreads / 32];
     const BlkDev& B = blks[blockIdx.z];
     double* __restrict__ const base = B.base;
     const double* __restrict__ const G = B.base;
     const double* __restrict__ const FX = B.aux_fx;
+    pdl_wait();
+    pdl_trigger();
+    const int active = ctl->active;
     const int nx = lay.nx, ny = lay.ny, pitch = lay.pitch;
     const unsigned PL = lay.plane;
     const unsigned n = blockIdx.x * (unsigned)kSplitUpdateThreads + threadIdx.x;
     const int i = (int)(n / (unsigned)nx), j = (int)(n - (unsigned)i * (unsigned)nx);
     const bool live = i < ny;
+    const unsigned o = lay.at(live ? i : 0, live ? j : 0);
+    const int nt_ = plan.ntargets;
+    constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
     double tm = __longlong_as_double(0x7ff0000000000000ll);
+    double dI[4] = {0.0, 0.0, 0.0, 0.0}, s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+    double cdx = 1.0, cdy = 1.0, c0 = 0.0, c1 = 0.0, a_cell = 1.0;
     if (live) {
-        const unsigned o = lay.at(i, j);
-        const int nt_ = plan.ntargets;
 #if !defined(PYH_HOST_TWIN)
-        if (plan.push_ghost) {   // edge cells: cos / sin of their boundary faces (reflection walls) into the L1 now, needed by the ghost push at the end
+        if (plan.push_ghost && (i == 0 || i == ny - 1 || j == 0 || j == nx - 1)) {
+            // edge cells: what the ghost push at the end will need -- the block's boundary-condition / neighbour table and the
+            // cos / sin of the boundary faces (reflection walls) -- into the L1 now
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(&B.bc[0]));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(&B.send[0]));
             if (i == 0 || i == ny - 1) {
                 const unsigned of = lay.at(i == 0 ? 0 : ny, j);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(G + po.ch + of));
@@ -294,8 +307,7 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             }
         }
 #endif
-        const double a = PYH_RO(G[po.A + o]);
-        double dI[4], s0[4], s1[4];
+        a_cell = PYH_RO(G[po.A + o]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const double IWp = FX[k * (size_t)PL + o], IEp = FX[k * (size_t)PL + o + 1];
@@ -304,9 +316,16 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             s1[k] = (nt_ > 1) ? base[plan.t[1].src + k * PL + o] : 0.0;
             dI[k] = IWp - IEp + ISp - INp;
         }
-        double cdx = 1.0, cdy = 1.0;
         if (plan.fuse_dt) { cdx = PYH_RO(G[po.cdx + o]); cdy = PYH_RO(G[po.cdy + o]); }
-        // D: residual (fvm/base.py:141-165) + RK partial sums (explicit_runge_kutta.py:66-89), as in k_stage_march
+        // dt * a[s][k] of the two static targets, requested with everything else (k_dt_finalize wrote them before this stage began)
+        const double k0 = (nt_ > 0) ? ctl->coef[plan.t[0].coef] : 0.0, k1 = (nt_ > 1) ? ctl->coef[plan.t[1].coef] : 0.0;
+        c0 = PYH_FOLD_POW2 ? rscale * k0 : k0;
+        c1 = PYH_FOLD_POW2 ? rscale * k1 : k1;
+    }
+    if (!active) return;   // same for every thread of the grid (the step lies beyond t_final, or the run went bad), taken with all loads in flight
+    if (live) {
+        const double a = a_cell;
+        // D: residual (fvm/base.py:141-165), as in k_stage_march
         double Rk[4];
         auto resid = [&](auto tag) -> bool {
             constexpr bool FAST = decltype(tag)::value;
@@ -323,10 +342,9 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             return ok;
         };
         if (!resid(FastTag{})) resid(SafeTag{});
-        constexpr double rscale = PYH_FOLD_POW2 ? 0.5 : 1.0;   // Rk == R / rscale
+        // RK partial sums (explicit_runge_kutta.py:66-89)
         double un[4] = {0.0, 0.0, 0.0, 0.0};
         if (nt_ > 0) {
-            const double c0 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[0].coef] : ctl->coef[plan.t[0].coef];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 un[k] = plan.t[0].add ? s0[k] + c0 * Rk[k] : s0[k];
@@ -334,16 +352,21 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             }
         }
         if (nt_ > 1) {   // targets 0 and 1 by static index (no local copy of the plan), the rare rest by a loop
-            const double c1 = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[1].coef] : ctl->coef[plan.t[1].coef];
 #pragma unroll
             for (int k = 0; k < 4; ++k) base[plan.t[1].dst + k * PL + o] = plan.t[1].add ? s1[k] + c1 * Rk[k] : s1[k];
         }
-        for (int q = 2; q < nt_; ++q) {   // tableaux with more than two live rows (e.g. DormandPrince5)
-            const double cq = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[q].coef] : ctl->coef[plan.t[q].coef];
+        if (nt_ > 2) {   // tableaux with more than two live rows (e.g. DormandPrince5); unrolled: a run-time index into the kernel
+                         // parameter `plan` would make every thread copy it to local memory first (17 stores at the top of the kernel)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double src = base[plan.t[q].src + k * PL + o];
-                base[plan.t[q].dst + k * PL + o] = plan.t[q].add ? src + cq * Rk[k] : src;
+            for (int q = 2; q < PYH_MAX_STAGES; ++q) {
+                if (q < nt_) {
+                    const double cq = PYH_FOLD_POW2 ? rscale * ctl->coef[plan.t[q].coef] : ctl->coef[plan.t[q].coef];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double src = base[plan.t[q].src + k * PL + o];
+                        base[plan.t[q].dst + k * PL + o] = plan.t[q].add ? src + cq * Rk[k] : src;
+                    }
+                }
             }
         }
         if (plan.fuse_dt && nt_ > 0) {
@@ -366,9 +389,9 @@ k_split_update(const BlkDev* __restrict__ blks, const Layout lay, const PlaneOff
             if (!(un[0] > 0.0) || !(un[3] > 0.0) || (tm != tm)) tm = __longlong_as_double(0xfff0000000000000ll);
         }
         if (plan.push_ghost && nt_ > 0) {
-            // ghost cells mirroring an edge cell this thread has just written (target 0 is the stage's output state)
+            // ghost cells mirroring an edge cell this thread has just written (target 0 is the stage's output state): from registers
+            // (no re-read of the value just stored); table and wall geometry were prefetched at the top
             const unsigned dst = plan.t[0].dst;
-            // from registers (no re-read of the value just stored); the wall geometry was prefetched at the top
             if (i == 0 || i == ny - 1) push_ghost_values(blks, B, lay, po, dst, i, j, true, un[0], un[1], un[2], un[3]);
             if (j == 0 || j == nx - 1) push_ghost_values(blks, B, lay, po, dst, i, j, false, un[0], un[1], un[2], un[3]);
         }

@@ -188,7 +188,7 @@ struct Twin {
             launch(dim3(cdivu(nfaces, kSplitFluxThreads), 2, nblk), kSplitFluxThreads, false,
                    [&] { fn_flux(blks.data(), lay, po, plan.cur, &ctl, C); });
             launch(dim3(cdivu((long long)nx * ny, kSplitUpdateThreads), 1, nblk), kSplitUpdateThreads, true,
-                   [&] { k_split_update(blks.data(), lay, po, plan, &ctl, &ctl, C); });
+                   [&] { k_split_update<5>(blks.data(), lay, po, plan, &ctl, &ctl, C); });
             ++g_split_stages;
             return;
         }

@@ -478,6 +478,7 @@ def run_ours(args):
     eng.transfers_sync()
     barrier()
     e2e_s = time.perf_counter() - t0
+    stage_path_info = (eng.stage_path(), dict(zip(("fused", "split"), eng.stage_path_tuning())))   # which kernels ran the stages (pyh_stage_path)
     eng.close()
 
     # max over ranks
@@ -530,6 +531,8 @@ def run_ours(args):
             "timed_call": "pyh_run (the device-resident loop Euler2D._solve drives): one CUDA graph per time step",
             "realizable_after_run": bool(ok),
             "setup_s": {k_: round(v, 3) for k_, v in setup.items()},
+            "stage_path": stage_path_info[0],   # 'fused' at the headline size (33.5 M cells per GPU are outside the split stage's range)
+            "stage_path_tuning_ms": stage_path_info[1],
         },
         "e2e": {
             "value": e2e_value, "unit": "cell-stage updates/s",

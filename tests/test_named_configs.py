@@ -116,11 +116,21 @@ def test_named_config_at_named_size_reproduces_the_reference(name, stage_path):
 
 @pytest.mark.parametrize("name", [n for n in ALL_NAMED if n != "ws2048"])   # ws2048 IS the oracle's output (3 minutes of numpy)
 def test_oracle_restatement_at_named_size_first_checkpoint(name):
+    if name == "ws1024" and not os.environ.get("PYH_NAMED_ORACLE_ALL"):
+        pytest.skip("half a minute of numpy on one 1024 x 1024 block: set PYH_NAMED_ORACLE_ALL=1 (the GPU suite replays it against the same fingerprint)")
     fp = Named(name)
     n = fp.meta["checkpoints"][0]
     if name.startswith("wedge"):
         n = fp.meta["checkpoints"][-1]          # 2 x 60^2: all 50 steps cost a second
     prob = cases.build_oracle(fp.blocks, fp.nx, fp.ny, fp.ic, **fp.scheme())
+    short = {"dmr": 2, "jet": 2}.get(name)       # a million cells per step in numpy: half a minute each to the first checkpoint
+    if short and not os.environ.get("PYH_NAMED_ORACLE_ALL"):
+        # default suite: the first steps only, checked through the dt sequence -- every dt is the CFL minimum over the WHOLE state the
+        # step before produced (the digests sit at the checkpoint; the full replay runs with PYH_NAMED_ORACLE_ALL=1, last run:
+        # profiles/r02r_named_twin.txt, and the GPU suite replays these cases to every checkpoint against the same fingerprints)
+        t, dts = prob.run(0.0, fp.meta["t_final_nd"], max_steps=short)
+        assert np.array_equal(np.asarray(dts), fp.dts[:short])
+        return
     t, dts = prob.run(0.0, fp.meta["t_final_nd"], max_steps=n)
     assert np.array_equal(np.asarray(dts), fp.dts[:n])
     fp.check(n, {g: prob.blocks[g].U for g in fp.gids})

@@ -75,3 +75,37 @@ def test_live_nrm2_matches_numba_linalg_norm():
     rng = np.random.default_rng(3)
     v = rng.standard_normal((50000, 4)) * 10.0 ** rng.integers(-8, 8, size=(50000, 1))
     assert np.array_equal(norms(v), mo.nrm2_x87(v))
+
+
+def test_live_shockbox_nan_of_the_limiter_and_the_abort():
+    """examples/shockbox as shipped: in step 24 the Venkatakrishnan quotient of an overflowing slope is inf / inf and
+    np.minimum.reduce carries the NaN into phi (limiters/base.py:179-186).  The oracle must put its NaNs where the reference
+    does -- same cells, same step -- and both must refuse the state (Euler2D.py:144-152); the kernels are held to the oracle's
+    NaN cells by tests/test_named_configs.py and tests/test_host_twin.py."""
+    from make_golden import ref_blocks
+
+    blocks, ic = cases.em_mesh(1, 1, 10.0, 10.0), cases.shockbox_ic
+
+    class IC:
+        def apply_to_block(self, block):
+            block.state.data = np.ascontiguousarray(ic(block.mesh.x[:, :, 0], block.mesh.y[:, :, 0]))
+
+    config = rh.make_config(nx=50, ny=50, initial_condition=IC(), time_integrator="RK2", CFL=0.4, t_final=2.0)
+    run = rh.RefRun(config, ref_blocks(blocks))
+    prob = cases.build_oracle(blocks, 50, 50, ic, flux="Roe", limiter="Venkatakrishnan", recon="conservative", integrator="RK2", CFL=0.4)
+    run.step(23)
+    t, dts = prob.run(0.0, 1e9, max_steps=23)
+    assert dts == run.dts
+    g = sorted(prob.blocks)[0]
+    assert np.array_equal(prob.blocks[g].U, run.blocks[0].state.data) and not np.isnan(prob.blocks[g].U).any()
+    s = run.solver
+    dt = s.get_dt()
+    with np.errstate(all="ignore"):
+        s._update_solution_blocks(dt=dt)                  # step 24 without the reference's own check ...
+        prob.step(prob.get_dt(t, 1e9))
+    Uref = run.blocks[0].state.data
+    assert np.isnan(Uref).sum() == 16
+    assert np.array_equal(prob.blocks[g].U, Uref, equal_nan=True)
+    assert not prob.realizable()
+    with pytest.raises(SystemExit):                        # ... which aborts (the stub MPI's Abort)
+        s._realizability_check()

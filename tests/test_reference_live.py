@@ -109,3 +109,31 @@ def test_live_shockbox_nan_of_the_limiter_and_the_abort():
     assert not prob.realizable()
     with pytest.raises(SystemExit):                        # ... which aborts (the stub MPI's Abort)
         s._realizability_check()
+
+
+@pytest.mark.parametrize("flux", ["Roe", "HLLL", "HLLE"])
+def test_live_flux_functions_on_unrealizable_face_states_including_nan(flux):
+    """The reference's own flux objects on face states with negative pressure / density on one side: the oracle's fluxes -- the
+    yardstick the kernels' NaN behaviour is tested against (tests/test_host_twin.py) -- are the reference's, NaN for NaN."""
+    import test_host_twin as T
+    from pyhype.flux.HLLE import FluxHLLE
+    from pyhype.flux.HLLL import FluxHLLL
+    from pyhype.flux.Roe import FluxRoe
+    from pyhype.states.primitive import PrimitiveState
+
+    if flux == "HLLE":
+        rh.patch_hlle()       # never runs unpatched (SURVEY.md appendix B)
+    cfg = rh.make_config(nx=40, ny=30)
+    WL, WR = T.face_states(1200, seed=61)
+    rng = np.random.default_rng(62)
+    for Wp, lo in ((WL, 0), (WR, 1)):
+        sel = rng.integers(0, 6, len(Wp))
+        Wp[sel == lo, 3] *= -1.0
+        Wp[sel == 2 + lo, 0] *= -1.0
+    WL, WR = WL.reshape(30, 40, 4), WR.reshape(30, 40, 4)
+    f = FluxRoe(cfg, 39, 30) if flux == "Roe" else {"HLLL": FluxHLLL, "HLLE": FluxHLLE}[flux](cfg, nx=40, ny=30)
+    with np.errstate(all="ignore"):
+        ref = f(PrimitiveState(fluid=cfg.fluid, array=WL.copy()), PrimitiveState(fluid=cfg.fluid, array=WR.copy()))
+        mine = mo.FLUXES[flux](WL.copy(), WR.copy(), cases.GAMMA)
+    assert np.isnan(ref).any(axis=-1).mean() > 0.3
+    assert np.array_equal(mine, ref, equal_nan=True)

@@ -137,3 +137,19 @@ def test_live_flux_functions_on_unrealizable_face_states_including_nan(flux):
         mine = mo.FLUXES[flux](WL.copy(), WR.copy(), cases.GAMMA)
     assert np.isnan(ref).any(axis=-1).mean() > 0.3
     assert np.array_equal(mine, ref, equal_nan=True)
+
+
+def test_live_limiter_functions_including_overflowing_slopes():
+    """limiters/limiters.py:25-62 on slopes from 0 to 1e300 (Venkatakrishnan through its numba loop, the variant every example
+    runs): the oracle's four limiter functions are the reference's, overflow to inf / inf = NaN included."""
+    from pyhype.limiters.limiters import BarthJespersen, VanAlbada, VanLeer, Venkatakrishnan
+
+    rng = np.random.default_rng(7)
+    s = np.concatenate((np.zeros(8), rng.uniform(0, 6, 4000), 10.0 ** rng.uniform(-300, 300, 4000), [1.0, 2.0, 1e154, 1.4180058467152723e211, np.inf]))
+    s = s.reshape(-1, 1, 1)
+    with np.errstate(all="ignore"):
+        ref = {"Venkatakrishnan": Venkatakrishnan._venkata(s.copy()), "VanAlbada": VanAlbada._limiter_func(s.copy()),
+               "VanLeer": VanLeer._limiter_func(s.copy()), "BarthJespersen": BarthJespersen._limiter_func(s.copy())}
+        for name, r in ref.items():
+            assert np.array_equal(mo.LIMITERS[name](s.copy()), r, equal_nan=True), name
+    assert np.isnan(ref["Venkatakrishnan"]).sum() > 500 and np.isnan(ref["VanAlbada"]).sum() > 500
